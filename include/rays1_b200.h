@@ -1,0 +1,150 @@
+/*
+ * rays1_b200.h -- C ABI of the B200-native Rays1 trace loop (librays1_b200.so).
+ *
+ * The reference (montib/rays1bench) has no FFI layer: its boundary for this path is four free C++ functions in one
+ * translation unit (create_small/medium/large_scene, benchmark) plus main().  BASELINE.json's north_star asks for the
+ * scene builders to feed device buffers "through a thin C-ABI layer called from the C++ host code"; this header is
+ * that layer.  Part 1 is the device-facing ABI the host code binds; part 2 is the reference-shaped host surface
+ * exported with C linkage so that non-C++ callers (ctypes in tests/ and bench.py) can drive the same code the
+ * drop-in executable runs.  Plain pointers and sizes only; every function that can fail returns 0 on success and a
+ * negative code otherwise, with the message available from r1_last_error().  There is NO CPU fallback: every
+ * compute entry point fails with R1_ERR_CUDA when no sm_100 device / driver is present.
+ *
+ * file:line citations are relative to /root/reference/.
+ */
+#ifndef RAYS1_B200_H
+#define RAYS1_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define R1_ABI_VERSION 1
+
+enum {
+    R1_OK = 0,
+    R1_ERR_ARG = -1,    /* bad argument */
+    R1_ERR_STATE = -2,  /* call order (e.g. render before commit) */
+    R1_ERR_CUDA = -3,   /* CUDA runtime / driver error, or no device */
+    R1_ERR_LIMIT = -4   /* scene larger than the on-chip staging limit */
+};
+
+/* Material tags: replace the reference's virtual Material hierarchy (src/latest/rayweek1.cpp:131-136, 396-512). */
+enum { R1_MAT_NONE = -1, R1_MAT_LAMBERT = 0, R1_MAT_METAL = 1, R1_MAT_DIELECTRIC = 2 };
+
+/* Kernel variants measured against each other (north_star (2)). */
+enum {
+    R1_VARIANT_MEGAKERNEL = 0, /* persistent threads, per-lane path state machine, packed f32x2 scan */
+    R1_VARIANT_WAVEFRONT = 1,  /* generate / intersect / shade kernels over compacted ray queues */
+    R1_VARIANT_MEGAKERNEL_SCALAR = 2 /* same megakernel with a scalar FFMA scan (A/B for the packed scan) */
+};
+
+typedef struct r1_scene r1_scene; /* opaque: host SoA + per-device buffers */
+
+/* Replaces RESULT (src/common/common.h:36-45) with the extra fields the roofline needs. */
+typedef struct r1_result {
+    double elapsed_seconds; /* host steady_clock: call entry -> result bytes where the caller asked for them */
+    double kernel_ms;       /* CUDA events around the trace kernel(s) + resolve on the launching stream */
+    double trace_ms;        /* CUDA events around the dominant trace kernel alone */
+    uint64_t num_rays;      /* the reference's counting rule: one per color() call (rayweek1.cpp:517) */
+    uint64_t num_samples;   /* pixels rendered by this call x spp */
+    uint32_t launches;      /* kernels launched by this call */
+    uint32_t n_units;       /* (pixel, sample-chunk) work units handed out */
+} r1_result;
+
+typedef struct r1_render_params {
+    int32_t width, height;   /* full image; SCREEN_W / SCREEN_H (common.h:19-20) */
+    int32_t spp;             /* NUM_SAMPLES_PER_PIXEL (common.h:23-28) */
+    int32_t max_bounces;     /* MAX_BOUNCES (common.h:18) */
+    int32_t variant;         /* R1_VARIANT_* */
+    uint32_t seed;           /* global seed of the counter-based RNG */
+    int32_t rank, world;     /* this call renders the row tiles k with k % world == rank (world = 1: all rows) */
+    int32_t row_tile;        /* rows per interleaved tile; <= 0 -> 8 */
+    int32_t threads_per_block, blocks_per_sm; /* <= 0 -> tuned defaults */
+} r1_render_params;
+
+/* ---- part 1: device-facing ABI ------------------------------------------------------------------------------ */
+
+int r1_abi_version(void);
+const char *r1_last_error(void);
+/* Number of CUDA devices visible, or a negative error. */
+int r1_device_count(void);
+
+/* Scene storage: replaces SphereSOA + Camera + Scene (soa_sphere.h:14-69, rayweek1.cpp:364-394, 539-549). */
+r1_scene *r1_scene_create(uint32_t capacity_hint);
+void r1_scene_destroy(r1_scene *scene);
+/* Camera::init (rayweek1.cpp:366-379). */
+int r1_scene_set_camera(r1_scene *scene, const float lookfrom[3], const float lookat[3], const float vup[3], float vfov_deg,
+                        float aspect, float aperture, float focus_dist);
+/* SphereSOA::add (soa_sphere.cpp:70-85): stores radius*radius and radius > 0 ? 1/radius : 0.  Metal's `param` is the
+ * fuzz (clamped to <= 1 as the Metal ctor does, rayweek1.cpp:424), Dielectric's the refraction index.  Returns the
+ * sphere's index (>= 0) or a negative error. */
+int r1_scene_add_sphere(r1_scene *scene, float cx, float cy, float cz, float radius, int mat_kind, float r, float g, float b,
+                        float param);
+/* Pads with the reference's placeholder (radius 0 at 999999999, material none) to a multiple of `multiple`
+ * (rayweek1.cpp:575-576; SIMD_WIDTH = 8 there). */
+int r1_scene_pad(r1_scene *scene, uint32_t multiple);
+uint32_t r1_scene_count(const r1_scene *scene);
+/* Host copies of the SoA arrays, `count` entries each (albedo: 3 per sphere) -- for bit-parity checks. */
+int r1_scene_get_soa(const r1_scene *scene, float *cx, float *cy, float *cz, float *radius_sq, float *inv_radius, int32_t *kind,
+                     float *albedo, float *param);
+/* out[22] = origin, lower-left corner, horizontal, vertical, u, v, w (3 each), lens radius (rayweek1.cpp:388-393). */
+int r1_scene_get_camera(const r1_scene *scene, float *out);
+/* Uploads the scan / shading buffers to CUDA device `device` (replicated per device; may be called once per device). */
+int r1_scene_commit(r1_scene *scene, int device);
+
+/* The hot path: render_tile + color + hit + scatter for every pixel x sample of this rank's rows
+ * (rayweek1.cpp:722-782, 515-536, 152-339, 396-512), RGB8 out, row 0 = BOTTOM of the picture (rayweek1.cpp:750).
+ *
+ * r1_render: host buffer.  rgb_host holds the rank's rows packed top-of-partition first in ascending global row order
+ * (world = 1: the whole width*height*3 image); the device->host copy is inside elapsed_seconds. */
+int r1_render(r1_scene *scene, const r1_render_params *params, uint8_t *rgb_host, r1_result *result);
+/* r1_render_device: device buffers, asynchronous on `cuda_stream` (a cudaStream_t; NULL = default stream).
+ * d_rgb: r1_local_pixels()*3 bytes; d_num_rays: one uint64, zeroed and then accumulated by the kernels.  The caller
+ * owns both (e.g. torch CUDA tensors that a following NCCL gather / reduce reads).  result->num_rays is NOT filled. */
+int r1_render_device(r1_scene *scene, const r1_render_params *params, void *d_rgb, void *d_num_rays, void *cuda_stream,
+                     r1_result *result);
+/* Rows / pixels owned by `rank` under the interleaved row-tile partition, and the global row of local row `lr`. */
+int64_t r1_local_rows(int height, int row_tile, int rank, int world);
+int64_t r1_local_pixels(int width, int height, int row_tile, int rank, int world);
+int r1_global_row(int local_row, int row_tile, int rank, int world);
+
+/* Parity entry points (host buffers, n rays each, xyz interleaved) -- the device functions the kernels use. */
+/* Hitable::hit (rayweek1.cpp:152-339); index = -1 on a miss.  dir must be unit length (Ray ctor, :104-108). */
+int r1_trace_rays(r1_scene *scene, int n, const float *org, const float *dir, float t_min, float t_max, int variant,
+                  int32_t *index, float *t, float *p, float *normal);
+/* Material::scatter (rayweek1.cpp:403-409, 427-433, 470-511) with the random inputs injected: rand_sphere is the
+ * unit-ball sample, rand_u the [0,1) uniform. */
+int r1_scatter(r1_scene *scene, int n, const float *dir_in, const float *p, const float *normal, const int32_t *index,
+               const float *rand_sphere, const float *rand_u, int32_t *ok, float *atten, float *dir_out);
+/* Camera::getRay (rayweek1.cpp:381-386) with the lens-disk sample injected (disk: 2 per ray). */
+int r1_get_ray(r1_scene *scene, int n, const float *su, const float *tv, const float *disk, float *org, float *dir);
+/* First `n` draws of the counter-based generator for (pixel, sample, seed): raw u32 -- for distribution tests. */
+int r1_rng_draws(uint32_t pixel, uint32_t sample, uint32_t seed, int n, uint32_t *out);
+/* FP32 FMA throughput microbenchmark on `device`: independent FFMA chains (packed = 0) or FFMA2 (packed = 1).
+ * Returns TFLOP/s (FMA = 2) in *tflops and the SM clock it ran at in *sm_mhz_est (cycles / elapsed). */
+int r1_fma_peak(int device, int packed, double *tflops, double *sm_mhz_est);
+
+/* ---- part 2: the reference's host surface, C linkage ------------------------------------------------------------- */
+
+/* Workload the reference fixes at compile time (common.h:3-31), runtime here. Any field <= 0 keeps its default:
+ * 1280 x 720, 250 spp, 50 bounces, 1 GPU, megakernel. */
+int r1_host_configure(int width, int height, int spp, int max_bounces, int variant, int n_gpus, uint32_t seed);
+/* create_small_scene / create_medium_scene / create_large_scene (rayweek1.cpp:552, 582, 654) and the synthetic
+ * 4096-sphere stress scene by name: "small" | "medium" | "large" | "synth4096".
+ * Returns a Scene* (see rays1_host.h) or NULL. */
+void *r1_host_create_scene(const char *name);
+/* The r1_scene inside a host Scene (borrowed). */
+r1_scene *r1_host_scene_handle(void *scene);
+/* benchmark(scene, pixels, write_tga, scene_name) (rayweek1.cpp:845-927): renders, prints the reference's report block,
+ * deletes the scene, optionally writes out_<name>.tga (which swaps R/B in `pixels` in place, common.h:108-114). */
+int r1_host_benchmark(void *scene, uint8_t *pixels, int write_tga, const char *scene_name, double *elapsed_seconds,
+                      uint64_t *num_rays, double *kernel_ms);
+void r1_host_destroy_scene(void *scene);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAYS1_B200_H */

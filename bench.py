@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- Mrays/s of the Rays1 trace loop on N B200s (BASELINE.json: "Mrays/s (large scene) at 1/2/4/8 B200;
+% of FP32 FMA peak; vs host CPU").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload large|medium|small|large4k|synth4096]
+                  [--variant mega|wavefront|scalar] [--impl reference]
+  N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A step = one full render of the workload (every pixel x sample through generate -> scan -> shade -> resolve, and for
+N > 1 the framebuffer gather + ray-counter reduce).  `value` times the steps on the device (CUDA events on the launching
+stream, inputs resident in HBM, max over ranks); `e2e` times the reference-facing call -- create_large_scene() +
+benchmark(scene, pixels, ...) -- with HOST buffers (scene upload and framebuffer download inside).  `roofline` is the
+FP32-FMA roofline of the trace kernel (this path is compute-bound: <= 128 KB of sphere data lives in shared memory);
+`cpu_baseline` is the reference's own src/latest code (oracle/_ref, its TileRenderScheduler on all host threads) on a
+bounded sample.  One JSON line on stdout, printed by rank 0.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (scene, width, height, spp, max_bounces)  -- BASELINE.json configs
+    "small": ("small", 1280, 720, 250, 50),        # config 1
+    "medium": ("medium", 1280, 720, 250, 50),      # config 2
+    "large": ("large", 1280, 720, 250, 50),        # config 3 (the metric's configuration)
+    "large4k": ("large", 3840, 2160, 1024, 50),    # config 4
+    "synth4096": ("synth4096", 1280, 720, 250, 50) # config 5
+}
+METRIC = "Mrays/s (large scene)"
+NOMINAL_SM_MHZ = 1965.0
+
+
+def workload_label(name):
+    scene, w, h, spp, mb = WORKLOADS[name]
+    return "%s scene %dx%d %d spp depth %d" % (scene, w, h, spp, mb)
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.thread = [], None, None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        self.mark = 0
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        t1 = time.time()
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+        rows = [r for t, r in self.rows if self.t0 <= t <= t1 + 0.2 and len(r) >= 8]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[0]) for r in rows)
+        reasons = set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in rows:
+            for k, nm in enumerate(names):
+                if r[4 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": sorted(reasons), "samples": len(rows),
+                "power_w_max": max(float(r[2]) for r in rows)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def reference_step(ref, scene, w, h, spp):
+    _, rays, el = ref.render(scene, w, h, spp)  # the reference's own TileRenderScheduler on hardware_concurrency() threads
+    return rays, el
+
+
+def cpu_reference(workload, budget_s, steps, warmup):
+    """Times the reference's CPU implementation (oracle/_ref = unmodified src/latest compiled in place; the oracle port
+    for the 4096-sphere scene the reference cannot hold) on a bounded sample of the workload.  Returns per-step results."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from cpu_checkers import Oracle, RefLib
+    scene_name, w, h, spp, mb = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    if scene_name != "synth4096" and RefLib.available() and w * 9 == h * 16:
+        ref = RefLib()
+        kind, scene = "reference", ref.scene_create(scene_name)
+        cores = ref.hardware_concurrency()
+        run = lambda s: reference_step(ref, scene, w, h, s)  # noqa: E731
+    else:
+        orc = Oracle()
+        kind, scene = "port", orc.scene_create(scene_name, w, h)
+        def run(s):  # noqa: E306
+            _, rays, el = orc.render(scene, w, h, s, mb, threads=cores)
+            return rays, el
+    rays, el = run(1)  # calibration: one sample per pixel
+    sample_spp = int(max(1, min(spp, budget_s / max(el, 1e-3))))
+    results = [run(sample_spp) for _ in range(warmup + steps)][warmup:]
+    tot_rays, tot_s = sum(r for r, _ in results), sum(e for _, e in results)
+    return dict(kind=kind, cores=cores, sample="%s scene %dx%d at %d spp (%d of %d spp; Mrays/s does not depend on spp)" %
+                (scene_name, w, h, sample_spp, sample_spp, spp), value=tot_rays / tot_s / 1e6, ms_per_step=1e3 * tot_s / len(results),
+                rays_per_sample=tot_rays / (len(results) * w * h * sample_spp))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="large", choices=sorted(WORKLOADS))
+    ap.add_argument("--variant", default="mega", choices=["mega", "wavefront", "scalar"])
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work per reference step / baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != max(args.gpus, 1) and world > 1:
+        raise SystemExit("--gpus %d does not match WORLD_SIZE %d" % (args.gpus, world))
+    scene_name, W, H, SPP, MB = WORKLOADS[args.workload]
+    config = {"workload": workload_label(args.workload), "scene": scene_name, "width": W, "height": H, "spp": SPP, "max_bounces": MB,
+              "partition": "interleaved row tiles of 8 rows, tile k -> rank k %% %d" % world, "variant": args.variant,
+              "l2": "flushed between timed steps (256 MiB write); the kernel's inputs (<= 128 KB of spheres) are staged to shared memory"}
+
+    # -------------------------------------------------------------------------------------------- reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps, warmup = args.steps, max(args.warmup, 1)
+        r = cpu_reference(args.workload, args.cpu_budget, steps, warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "Mrays/s", "n_gpus": args.gpus, "steps": steps,
+                "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": r["value"], "unit": "Mrays/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0, "rays_per_sample": r["rays_per_sample"]}
+        print(json.dumps(line))
+        return
+
+    # -------------------------------------------------------------------------------------------- B200 arm
+    import torch
+    import torch.distributed as dist
+
+    import rays1bench_b200 as r1
+    from rays1bench_b200 import dist as r1d
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this path has no CPU implementation (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    variant = r1.VARIANTS[args.variant]
+    row_tile = 8
+    r1.configure(width=W, height=H, spp=SPP, max_bounces=MB, variant=variant, n_gpus=1, seed=0, quiet=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # resident inputs + output buffers (value arm): scene committed once, torch owns the output tensors
+    # the host builders commit to devices 0..n-1 of ONE process; under torchrun each rank commits to its own GPU
+    scene = r1.create_scene(scene_name, commit=False)
+    r1._check(r1.lib.r1_scene_commit(scene.handle, local_rank), "r1_scene_commit")
+    n_real = r1.REAL_SPHERES[scene_name]
+    n_pad = (scene.count() + 31) // 32 * 32
+
+    my_rows = r1.local_rows(H, row_tile, rank, world)
+    max_rows = r1d.max_local_rows(H, row_tile, world)
+    d_rgb = torch.zeros((max_rows, W, 3), dtype=torch.uint8, device=dev)
+    d_rays = torch.zeros(1, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    kw = dict(width=W, height=H, spp=SPP, max_bounces=MB, variant=variant, seed=0, rank=rank, world=world, row_tile=row_tile, device=local_rank)
+
+    def step():
+        """one pass of the hot path; returns (#kernels of ours launched, final image tensor on rank 0)"""
+        res = scene.render_device(d_rgb.data_ptr(), d_rays.data_ptr(), stream.cuda_stream, **kw)
+        launches = res.launches
+        img = d_rgb
+        if world > 1:
+            gathered = r1d.gather_framebuffer(d_rgb, H, row_tile, rank, world)
+            r1d.reduce_ray_count(d_rays, world)
+            if rank == 0:
+                img = r1d.deinterleave(gathered, W, H, row_tile, world)
+                launches += 1
+        return launches, img
+
+    total_ms, trace_ms, total_rays, launches = 0.0, 0.0, 0, 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = None
+    for it in range(args.warmup + args.steps):
+        timed = it >= args.warmup
+        if it == args.warmup:
+            sampler = ClockSampler(local_rank) if rank == 0 else None
+            if sampler:
+                sampler.begin()
+        flush.zero_()  # L2 flush between iterations (outside the timed events)
+        barrier()
+        e0.record(stream)
+        n_l, img = step()
+        e1.record(stream)
+        barrier()
+        if timed:
+            total_ms += e0.elapsed_time(e1)
+            trace_ms += scene.render_wait(local_rank).trace_ms
+            total_rays += int(d_rays.item()) if rank == 0 else 0  # for N > 1 the reduced total lives on rank 0
+            launches += n_l
+    clocks = sampler.end() if sampler else None
+    ms_value = allmax(total_ms)        # max over ranks of the summed per-step device times
+    ms_trace = allmax(trace_ms)
+
+    # ---- e2e: the reference-facing call with HOST buffers, every step = scene upload + render + download
+    pixels_t = torch.zeros((H, W, 3), dtype=torch.uint8).pin_memory()
+    pixels = pixels_t.numpy()
+    h2d = n_pad * (32 + 4 + 16 + 4)
+    d2h = W * H * 3 + 8
+    e2e_s, e2e_rays = 0.0, 0
+    for it in range(args.warmup + args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        if world == 1:
+            sc = r1.create_scene(scene_name)                   # builders emit the device buffers (H2D)
+            res = r1.benchmark(sc, pixels, False, scene_name)  # render + D2H into the caller's pixels; consumes the scene
+            rays_step = res.num_rays
+        else:
+            sc = r1.create_scene(scene_name, commit=False)
+            r1._check(r1.lib.r1_scene_commit(sc.handle, local_rank), "r1_scene_commit")  # H2D on this rank's GPU
+            sc.render_device(d_rgb.data_ptr(), d_rays.data_ptr(), stream.cuda_stream, **kw)
+            gathered = r1d.gather_framebuffer(d_rgb, H, row_tile, rank, world)
+            r1d.reduce_ray_count(d_rays, world)
+            rays_step = 0
+            if rank == 0:
+                img = r1d.deinterleave(gathered, W, H, row_tile, world)
+                pixels_t.copy_(img, non_blocking=True)         # D2H of the RGB8 image into pinned host memory
+                rays_step = int(d_rays.cpu().item())
+            torch.cuda.synchronize()
+            sc.close()
+        dt = time.perf_counter() - t0
+        dt = allmax(dt)
+        if it >= args.warmup:
+            e2e_s += dt
+            e2e_rays += rays_step
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (FP32 FMA pipe)
+    f_ray = r1.flops_per_ray(n_real)
+    peak_scalar, mhz_est = r1.fma_peak(local_rank, packed=False)
+    peak_packed, _ = r1.fma_peak(local_rank, packed=True)
+    peak_meas = max(peak_scalar, peak_packed)
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    peak_nominal = sm_count * 128 * 2 * NOMINAL_SM_MHZ * 1e6 / 1e12
+    achieved = total_rays * f_ray / (ms_trace * 1e-3) / 1e12 / world  # per GPU
+    n_chunks = (SPP + max(8, (SPP + 15) // 16) - 1) // max(8, (SPP + 15) // 16)
+    hbm_bytes = W * H * (n_chunks * 16 * 2 + 3) + n_pad * 32 * sm_count
+    roofline = {"bound": "fp32_fma", "kernel": "r1::megakernel" if args.variant != "wavefront" else "r1::wf_intersect", "achieved": achieved,
+                "peak": peak_meas, "unit": "TFLOP/s", "frac": achieved / peak_meas,
+                "peak_source": "FFMA/FFMA2 chain microbenchmark on this GPU (r1_fma_peak), per GPU; scalar %.1f / packed %.1f TFLOP/s at ~%.0f MHz" %
+                               (peak_scalar, peak_packed, mhz_est),
+                "peak_nominal": peak_nominal, "frac_nominal": achieved / peak_nominal,
+                "flops_per_ray": f_ray, "flops_model": "16 per ray-sphere test (FMA=2) x %d real spheres + 70 shading (SURVEY.md 8d)" % n_real,
+                "traffic": None,
+                "hbm": {"algorithmic_bytes_per_step": hbm_bytes, "achieved_gbs": hbm_bytes * args.steps / (ms_trace * 1e-3) / 1e9,
+                        "note": "partial sums written + read once, RGB8 out, sphere staging per CTA: HBM is idle on this path"}}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        roofline["hbm"]["peak_gbs"] = peaks.get("hbm_gbs")
+    except (OSError, ValueError):
+        pass
+
+    line = {"metric": METRIC, "value": total_rays / (ms_value * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "api": "create_%s_scene() + benchmark(scene, pixels, write_tga=False, name)" % scene_name if world == 1 else
+                           "per rank: scene commit + r1_render_device; NCCL gather + reduce; rank 0 de-interleave + D2H"},
+            "gpu_launches": launches, "roofline": roofline,
+            "kernel_only": {"trace_ms_per_step": ms_trace / args.steps, "mrays_per_s": total_rays / (ms_trace * 1e-3) / 1e6},
+            "rays_per_step": total_rays // args.steps, "rays_per_sample": total_rays / (args.steps * W * H * SPP)}
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference(args.workload, args.cpu_budget, 1, 0)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "Mrays/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

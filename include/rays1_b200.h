@@ -62,7 +62,8 @@ typedef struct r1_render_params {
     uint32_t seed;           /* global seed of the counter-based RNG */
     int32_t rank, world;     /* this call renders the row tiles k with k % world == rank (world = 1: all rows) */
     int32_t row_tile;        /* rows per interleaved tile; <= 0 -> 8 */
-    int32_t threads_per_block, blocks_per_sm; /* <= 0 -> tuned defaults */
+    int32_t blocks_per_sm;   /* persistent CTAs per SM; <= 0 -> tuned default */
+    int32_t device;          /* CUDA device to run on (must have been committed); < 0 -> device of the last commit */
 } r1_render_params;
 
 /* ---- part 1: device-facing ABI ------------------------------------------------------------------------------ */
@@ -106,10 +107,18 @@ int r1_render(r1_scene *scene, const r1_render_params *params, uint8_t *rgb_host
  * owns both (e.g. torch CUDA tensors that a following NCCL gather / reduce reads).  result->num_rays is NOT filled. */
 int r1_render_device(r1_scene *scene, const r1_render_params *params, void *d_rgb, void *d_num_rays, void *cuda_stream,
                      r1_result *result);
+/* Blocks until the last r1_render_device of this scene on `device` (< 0: device of the last commit) has finished and
+ * fills kernel_ms / trace_ms (CUDA events recorded on the launching stream), launches, n_units, num_samples. */
+int r1_render_wait(r1_scene *scene, int device, r1_result *result);
 /* Rows / pixels owned by `rank` under the interleaved row-tile partition, and the global row of local row `lr`. */
 int64_t r1_local_rows(int height, int row_tile, int rank, int world);
 int64_t r1_local_pixels(int width, int height, int row_tile, int rank, int world);
 int r1_global_row(int local_row, int row_tile, int rank, int world);
+
+/* Multi-GPU epilogue on the gathering device: `d_gathered` holds `world` slices of `stride` bytes, slice r = rank r's
+ * packed local rows; writes the full width*height*3 image (row 0 = bottom) to d_out.  Asynchronous on cuda_stream. */
+int r1_deinterleave_rows(int device, const void *d_gathered, uint64_t stride, void *d_out, int width, int height, int row_tile,
+                         int world, void *cuda_stream);
 
 /* Parity entry points (host buffers, n rays each, xyz interleaved) -- the device functions the kernels use. */
 /* Hitable::hit (rayweek1.cpp:152-339); index = -1 on a miss.  dir must be unit length (Ray ctor, :104-108). */
@@ -132,10 +141,13 @@ int r1_fma_peak(int device, int packed, double *tflops, double *sm_mhz_est);
 /* Workload the reference fixes at compile time (common.h:3-31), runtime here. Any field <= 0 keeps its default:
  * 1280 x 720, 250 spp, 50 bounces, 1 GPU, megakernel. */
 int r1_host_configure(int width, int height, int spp, int max_bounces, int variant, int n_gpus, uint32_t seed);
+/* Non-zero: benchmark() does not print its report block (callers that print their own). */
+int r1_host_set_quiet(int quiet);
 /* create_small_scene / create_medium_scene / create_large_scene (rayweek1.cpp:552, 582, 654) and the synthetic
  * 4096-sphere stress scene by name: "small" | "medium" | "large" | "synth4096".
- * Returns a Scene* (see rays1_host.h) or NULL. */
-void *r1_host_create_scene(const char *name);
+ * commit != 0 also uploads the device buffers to GPUs 0 .. n_gpus-1 (what the C++ builders always do); commit == 0
+ * builds the host SoA only.  Returns a Scene* (see rays1_host.h) or NULL (r1_last_error() says why). */
+void *r1_host_create_scene(const char *name, int commit);
 /* The r1_scene inside a host Scene (borrowed). */
 r1_scene *r1_host_scene_handle(void *scene);
 /* benchmark(scene, pixels, write_tga, scene_name) (rayweek1.cpp:845-927): renders, prints the reference's report block,
@@ -143,6 +155,11 @@ r1_scene *r1_host_scene_handle(void *scene);
 int r1_host_benchmark(void *scene, uint8_t *pixels, int write_tga, const char *scene_name, double *elapsed_seconds,
                       uint64_t *num_rays, double *kernel_ms);
 void r1_host_destroy_scene(void *scene);
+/* tga_write_rgb24 (common.h:86-122): 18-byte header, type 2, 24 bpp, bottom-left origin; swaps R and B in `pixels`. */
+int r1_host_write_tga(const char *filename, int width, int height, uint8_t *pixels);
+/* log_results (common.h:47-77): out_<scene>.txt = "version|%.3fs|<rays>|%0.3f mrays/s|" averaged over the runs. */
+int r1_host_log_results(const char *version, const char *scene, const double *elapsed_seconds, const uint64_t *num_rays,
+                        int num_runs);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,611 @@
+// r1_core.cu -- implementation of the device-facing C ABI (include/rays1_b200.h part 1): scene storage, upload,
+// render orchestration on one device, parity entry points.  No CPU fallback anywhere: every compute entry point
+// returns R1_ERR_CUDA if the CUDA runtime reports an error (including "no device").
+// file:line citations are relative to /root/reference/.
+#include "../../include/rays1_b200.h"
+#include "r1_kernels.cuh"
+#include "r1_wavefront.cuh"
+
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define R1_CUDA(expr)                                                                                        \
+    do {                                                                                                     \
+        cudaError_t e_ = (expr);                                                                             \
+        if (e_ != cudaSuccess) return fail(R1_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// Per-device state of a committed scene.  Scratch buffers grow on demand and are reused across renders.
+struct DeviceCtx {
+    int device = -1;
+    int sm_count = 0;
+    float4 *spheres = nullptr;  // [scan | exact], n_pad * 2 float4
+    float *inv_radius = nullptr;
+    float4 *mat = nullptr;
+    int32_t *kind = nullptr;
+    r1::DevScene dev;
+    float4 *partial = nullptr; size_t partial_cap = 0;
+    unsigned int *unit_counter = nullptr;
+    uint8_t *rgb = nullptr; size_t rgb_cap = 0;
+    unsigned long long *num_rays = nullptr;
+    r1::WavefrontBuffers wf;
+    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    cudaStream_t last_stream = nullptr;
+    uint32_t last_launches = 0, last_units = 0;
+    uint64_t last_samples = 0;
+};
+
+}  // namespace
+
+struct r1_scene {
+    // SphereSOA (soa_sphere.h:38-53) with the Material hierarchy flattened to (kind, albedo, param)
+    std::vector<float> cx, cy, cz, radius_sq, inv_radius, albedo, param;
+    std::vector<int32_t> kind;
+    r1::Camera cam;
+    bool have_camera = false;
+    std::map<int, DeviceCtx> ctx;
+    int current = -1;  // device of the last commit
+};
+
+namespace {
+
+void free_ctx(DeviceCtx &c)
+{
+    if (c.device < 0) return;
+    cudaSetDevice(c.device);
+    cudaFree(c.spheres); cudaFree(c.inv_radius); cudaFree(c.mat); cudaFree(c.kind);
+    cudaFree(c.partial); cudaFree(c.unit_counter); cudaFree(c.rgb); cudaFree(c.num_rays);
+    r1::wavefront_free(c.wf);
+    for (auto &e : c.ev) if (e) cudaEventDestroy(e);
+    c = DeviceCtx();
+}
+
+void v3_unit(float *v)
+{
+    const float inv = 1.0f / std::sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
+    v[0] *= inv; v[1] *= inv; v[2] *= inv;
+}
+
+template <typename T>
+int grow(T *&ptr, size_t &cap, size_t need)
+{
+    if (need <= cap) return R1_OK;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr; cap = 0;
+    R1_CUDA(cudaMalloc(&ptr, need * sizeof(T)));
+    cap = need;
+    return R1_OK;
+}
+
+int get_ctx(r1_scene *scene, DeviceCtx **out, int device = -1)
+{
+    if (!scene) return fail(R1_ERR_ARG, "null scene");
+    if (device < 0) device = scene->current;
+    auto it = scene->ctx.find(device);
+    if (device < 0 || it == scene->ctx.end()) return fail(R1_ERR_STATE, "scene not committed to device %d (call r1_scene_commit)", device);
+    R1_CUDA(cudaSetDevice(device));
+    *out = &it->second;
+    return R1_OK;
+}
+
+// samples per unit: a function of spp ONLY (see RenderArgs) -- at most 16 chunks per pixel, at least 8 samples each
+int samples_per_unit(int spp) { return std::max(8, (spp + 15) / 16); }
+
+struct Partition { int local_rows; uint32_t npix_local; };
+
+Partition partition(int width, int height, int row_tile, int rank, int world)
+{
+    Partition p;
+    p.local_rows = (int)r1_local_rows(height, row_tile, rank, world);
+    p.npix_local = (uint32_t)p.local_rows * (uint32_t)width;
+    return p;
+}
+
+template <bool kPacked, bool kStaged>
+int launch_megakernel(const DeviceCtx &c, const r1::RenderArgs &args, const r1_render_params &prm, cudaStream_t stream)
+{
+    // 512 threads x 1 CTA per SM: 16 warps/SM = 4 per scheduler; shared memory = 16 + n_pad * 32 bytes.
+    constexpr int kThreads = 512, kBlocks = 1;
+    auto kern = r1::megakernel<kPacked, kStaged, kThreads, kBlocks>;
+    const size_t smem = kStaged ? 16 + (size_t)args.scene.n_pad * 32 : 0;
+    R1_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = c.sm_count * kBlocks;
+    if (prm.blocks_per_sm > 0) grid = c.sm_count * prm.blocks_per_sm;
+    // never launch more lanes than there are units
+    const long long max_ctas = ((long long)args.n_units + kThreads - 1) / kThreads;
+    if (grid > max_ctas) grid = (int)std::max<long long>(1, max_ctas);
+    kern<<<grid, kThreads, smem, stream>>>(args);
+    R1_CUDA(cudaGetLastError());
+    return R1_OK;
+}
+
+int validate(const r1_render_params *p)
+{
+    if (!p) return fail(R1_ERR_ARG, "null params");
+    if (p->width <= 0 || p->height <= 0 || p->spp <= 0 || p->max_bounces < 0) return fail(R1_ERR_ARG, "width/height/spp must be > 0, max_bounces >= 0");
+    if (p->world <= 0 || p->rank < 0 || p->rank >= p->world) return fail(R1_ERR_ARG, "bad rank/world %d/%d", p->rank, p->world);
+    if ((uint64_t)p->width * (uint64_t)p->height > (1ull << 31)) return fail(R1_ERR_ARG, "image too large");
+    if (p->variant < 0 || p->variant > 2) return fail(R1_ERR_ARG, "unknown variant %d", p->variant);
+    return R1_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int r1_abi_version(void) { return R1_ABI_VERSION; }
+const char *r1_last_error(void) { return g_error.c_str(); }
+
+int r1_device_count(void)
+{
+    int n = 0;
+    R1_CUDA(cudaGetDeviceCount(&n));
+    return n;
+}
+
+r1_scene *r1_scene_create(uint32_t capacity_hint)
+{
+    r1_scene *s = new r1_scene();
+    memset(&s->cam, 0, sizeof(s->cam));
+    s->cx.reserve(capacity_hint); s->cy.reserve(capacity_hint); s->cz.reserve(capacity_hint);
+    s->radius_sq.reserve(capacity_hint); s->inv_radius.reserve(capacity_hint);
+    s->albedo.reserve(3 * (size_t)capacity_hint); s->param.reserve(capacity_hint); s->kind.reserve(capacity_hint);
+    return s;
+}
+
+void r1_scene_destroy(r1_scene *scene)
+{
+    if (!scene) return;
+    for (auto &kv : scene->ctx) free_ctx(kv.second);
+    delete scene;
+}
+
+// Camera::init (rayweek1.cpp:366-379)
+int r1_scene_set_camera(r1_scene *scene, const float lookfrom[3], const float lookat[3], const float vup[3], float vfov_deg, float aspect,
+                        float aperture, float focus_dist)
+{
+    if (!scene || !lookfrom || !lookat || !vup) return fail(R1_ERR_ARG, "null argument");
+    r1::Camera &c = scene->cam;
+    c.lens_radius = aperture / 2;
+    const float theta = vfov_deg * (float)M_PI / 180;
+    const float half_height = tanf(theta / 2);
+    const float half_width = aspect * half_height;
+    for (int k = 0; k < 3; ++k) { c.origin[k] = lookfrom[k]; c.w[k] = lookfrom[k] - lookat[k]; }
+    v3_unit(c.w);
+    c.u[0] = vup[1] * c.w[2] - vup[2] * c.w[1];
+    c.u[1] = vup[2] * c.w[0] - vup[0] * c.w[2];
+    c.u[2] = vup[0] * c.w[1] - vup[1] * c.w[0];
+    v3_unit(c.u);
+    c.v[0] = c.w[1] * c.u[2] - c.w[2] * c.u[1];
+    c.v[1] = c.w[2] * c.u[0] - c.w[0] * c.u[2];
+    c.v[2] = c.w[0] * c.u[1] - c.w[1] * c.u[0];
+    for (int k = 0; k < 3; ++k) {
+        c.llc[k] = ((c.origin[k] - (half_width * focus_dist) * c.u[k]) - (half_height * focus_dist) * c.v[k]) - focus_dist * c.w[k];
+        c.horizontal[k] = (2 * half_width * focus_dist) * c.u[k];
+        c.vertical[k] = (2 * half_height * focus_dist) * c.v[k];
+    }
+    scene->have_camera = true;
+    return R1_OK;
+}
+
+// SphereSOA::add (soa_sphere.cpp:70-85)
+int r1_scene_add_sphere(r1_scene *scene, float cx, float cy, float cz, float radius, int mat_kind, float r, float g, float b, float param)
+{
+    if (!scene) return fail(R1_ERR_ARG, "null scene");
+    if (mat_kind < R1_MAT_NONE || mat_kind > R1_MAT_DIELECTRIC) return fail(R1_ERR_ARG, "unknown material kind %d", mat_kind);
+    if (mat_kind == R1_MAT_NONE && radius > 0) return fail(R1_ERR_ARG, "a sphere with radius > 0 needs a material");
+    if (mat_kind == R1_MAT_METAL) param = param < 1 ? param : 1;  // Metal ctor, rayweek1.cpp:424
+    scene->cx.push_back(cx); scene->cy.push_back(cy); scene->cz.push_back(cz);
+    scene->radius_sq.push_back(radius * radius);
+    scene->inv_radius.push_back(radius > 0 ? (1.0f / radius) : 0);
+    scene->kind.push_back(mat_kind);
+    scene->albedo.push_back(r); scene->albedo.push_back(g); scene->albedo.push_back(b);
+    scene->param.push_back(param);
+    return (int)scene->cx.size() - 1;
+}
+
+int r1_scene_pad(r1_scene *scene, uint32_t multiple)
+{
+    if (!scene || multiple == 0) return fail(R1_ERR_ARG, "bad argument");
+    while (scene->cx.size() % multiple != 0) {
+        int rc = r1_scene_add_sphere(scene, 999999999.0f, 999999999.0f, 999999999.0f, 0.0f, R1_MAT_NONE, 0, 0, 0, 0);
+        if (rc < 0) return rc;
+    }
+    return R1_OK;
+}
+
+uint32_t r1_scene_count(const r1_scene *scene) { return scene ? (uint32_t)scene->cx.size() : 0; }
+
+int r1_scene_get_soa(const r1_scene *scene, float *cx, float *cy, float *cz, float *radius_sq, float *inv_radius, int32_t *kind, float *albedo,
+                     float *param)
+{
+    if (!scene) return fail(R1_ERR_ARG, "null scene");
+    const size_t n = scene->cx.size();
+    memcpy(cx, scene->cx.data(), n * 4); memcpy(cy, scene->cy.data(), n * 4); memcpy(cz, scene->cz.data(), n * 4);
+    memcpy(radius_sq, scene->radius_sq.data(), n * 4); memcpy(inv_radius, scene->inv_radius.data(), n * 4);
+    memcpy(kind, scene->kind.data(), n * 4); memcpy(albedo, scene->albedo.data(), 3 * n * 4); memcpy(param, scene->param.data(), n * 4);
+    return R1_OK;
+}
+
+int r1_scene_get_camera(const r1_scene *scene, float *out)
+{
+    if (!scene || !out) return fail(R1_ERR_ARG, "null argument");
+    const r1::Camera &c = scene->cam;
+    const float *src[7] = { c.origin, c.llc, c.horizontal, c.vertical, c.u, c.v, c.w };
+    for (int k = 0; k < 7; ++k) memcpy(out + 3 * k, src[k], 12);
+    out[21] = c.lens_radius;
+    return R1_OK;
+}
+
+int r1_scene_commit(r1_scene *scene, int device)
+{
+    if (!scene) return fail(R1_ERR_ARG, "null scene");
+    if (!scene->have_camera) return fail(R1_ERR_STATE, "camera not set");
+    if (scene->cx.empty()) return fail(R1_ERR_STATE, "scene has no spheres");
+    int ndev = 0;
+    R1_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(R1_ERR_ARG, "device %d out of range (%d visible)", device, ndev);
+    R1_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    R1_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(R1_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+
+    DeviceCtx &c = scene->ctx[device];
+    if (c.device >= 0) free_ctx(c);
+    c.device = device;
+    c.sm_count = prop.multiProcessorCount;
+
+    const int n = (int)scene->cx.size();
+    const int n_pad = (n + 31) / 32 * 32;
+    const float inf = std::numeric_limits<float>::infinity();
+    std::vector<float4> spheres(2 * (size_t)n_pad);
+    float *scan = reinterpret_cast<float *>(spheres.data());
+    for (int i = 0; i < n_pad; ++i) {
+        const bool real = i < n && scene->inv_radius[i] != 0;  // rayweek1.cpp:288-292: inv_radius == 0 spheres never hit
+        const int g = i / 4, k = i % 4;
+        scan[16 * g + 0 + k] = real ? -scene->cx[i] : 0.0f;
+        scan[16 * g + 4 + k] = real ? -scene->cy[i] : 0.0f;
+        scan[16 * g + 8 + k] = real ? -scene->cz[i] : 0.0f;
+        scan[16 * g + 12 + k] = real ? -(scene->radius_sq[i] * (1.0f + 1.0f / 256.0f)) : inf;
+        spheres[n_pad + i] = i < n ? make_float4(scene->cx[i], scene->cy[i], scene->cz[i], scene->radius_sq[i]) : make_float4(0, 0, 0, 0);
+    }
+    std::vector<float> inv_r(n_pad, 0.0f);
+    std::vector<float4> mat(n_pad, make_float4(0, 0, 0, 0));
+    std::vector<int32_t> kind(n_pad, R1_MAT_NONE);
+    for (int i = 0; i < n; ++i) {
+        inv_r[i] = scene->inv_radius[i];
+        mat[i] = make_float4(scene->albedo[3 * i], scene->albedo[3 * i + 1], scene->albedo[3 * i + 2], scene->param[i]);
+        kind[i] = scene->kind[i];
+    }
+    R1_CUDA(cudaMalloc(&c.spheres, spheres.size() * sizeof(float4)));
+    R1_CUDA(cudaMalloc(&c.inv_radius, n_pad * sizeof(float)));
+    R1_CUDA(cudaMalloc(&c.mat, n_pad * sizeof(float4)));
+    R1_CUDA(cudaMalloc(&c.kind, n_pad * sizeof(int32_t)));
+    R1_CUDA(cudaMalloc(&c.unit_counter, sizeof(unsigned int)));
+    R1_CUDA(cudaMalloc(&c.num_rays, sizeof(unsigned long long)));
+    R1_CUDA(cudaMemcpy(c.spheres, spheres.data(), spheres.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    R1_CUDA(cudaMemcpy(c.inv_radius, inv_r.data(), n_pad * sizeof(float), cudaMemcpyHostToDevice));
+    R1_CUDA(cudaMemcpy(c.mat, mat.data(), n_pad * sizeof(float4), cudaMemcpyHostToDevice));
+    R1_CUDA(cudaMemcpy(c.kind, kind.data(), n_pad * sizeof(int32_t), cudaMemcpyHostToDevice));
+    for (auto &e : c.ev) R1_CUDA(cudaEventCreate(&e));
+
+    c.dev.scan = c.spheres;
+    c.dev.exact = c.spheres + n_pad;
+    c.dev.inv_radius = c.inv_radius;
+    c.dev.mat = c.mat;
+    c.dev.kind = c.kind;
+    c.dev.n_pad = n_pad;
+    c.dev.n_real = n;
+    c.dev.cam = scene->cam;
+    scene->current = device;
+    return R1_OK;
+}
+
+int64_t r1_local_rows(int height, int row_tile, int rank, int world)
+{
+    if (row_tile <= 0) row_tile = 8;
+    int64_t rows = 0;
+    for (int k = rank, y = rank * row_tile; y < height; k += world, y += world * row_tile) rows += std::min(row_tile, height - y);
+    return rows;
+}
+
+int64_t r1_local_pixels(int width, int height, int row_tile, int rank, int world) { return r1_local_rows(height, row_tile, rank, world) * width; }
+
+int r1_global_row(int local_row, int row_tile, int rank, int world)
+{
+    if (row_tile <= 0) row_tile = 8;
+    return r1::global_row(local_row, row_tile, rank, world);
+}
+
+int r1_deinterleave_rows(int device, const void *d_gathered, uint64_t stride, void *d_out, int width, int height, int row_tile, int world,
+                         void *cuda_stream)
+{
+    if (!d_gathered || !d_out || width <= 0 || height <= 0 || world <= 0) return fail(R1_ERR_ARG, "bad argument");
+    if (row_tile <= 0) row_tile = 8;
+    R1_CUDA(cudaSetDevice(device));
+    const size_t total = (size_t)width * height * 3;
+    const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+    r1::deinterleave_rows<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>((const uint8_t *)d_gathered, (size_t)stride, (uint8_t *)d_out, width, height,
+                                                                        row_tile, world);
+    R1_CUDA(cudaGetLastError());
+    return R1_OK;
+}
+
+int r1_render_device(r1_scene *scene, const r1_render_params *params, void *d_rgb, void *d_num_rays, void *cuda_stream, r1_result *result)
+{
+    int rc = validate(params);
+    if (rc) return rc;
+    DeviceCtx *cp = nullptr;
+    rc = get_ctx(scene, &cp, params->device);
+    if (rc) return rc;
+    DeviceCtx &c = *cp;
+    if (!d_rgb || !d_num_rays) return fail(R1_ERR_ARG, "null device buffer");
+    r1_render_params prm = *params;
+    if (prm.row_tile <= 0) prm.row_tile = 8;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+
+    const Partition part = partition(prm.width, prm.height, prm.row_tile, prm.rank, prm.world);
+    r1::RenderArgs a;
+    memset(&a, 0, sizeof(a));
+    a.scene = c.dev;
+    a.width = prm.width; a.height = prm.height; a.spp = prm.spp; a.max_bounces = prm.max_bounces;
+    a.rank = prm.rank; a.world = prm.world; a.row_tile = prm.row_tile;
+    a.npix_local = part.npix_local;
+    a.samples_per_unit = samples_per_unit(prm.spp);
+    a.n_chunks = (prm.spp + a.samples_per_unit - 1) / a.samples_per_unit;
+    const uint64_t n_units = (uint64_t)a.npix_local * (uint64_t)a.n_chunks;
+    if (n_units >= (1ull << 32) - (1ull << 24)) return fail(R1_ERR_LIMIT, "too many work units (%llu)", (unsigned long long)n_units);
+    a.n_units = (uint32_t)n_units;
+    a.seed = prm.seed;
+    a.inv_w = 1.0f / prm.width; a.inv_h = 1.0f / prm.height;  // rayweek1.cpp:746
+    a.inv_spp = (float)(1.0f / prm.spp);                       // rayweek1.cpp:765
+    a.rgb = (uint8_t *)d_rgb;
+    a.num_rays = (unsigned long long *)d_num_rays;
+    a.unit_counter = c.unit_counter;
+
+    c.last_stream = stream;
+    c.last_launches = 0;
+    c.last_units = a.n_units;
+    c.last_samples = (uint64_t)a.npix_local * (uint64_t)prm.spp;
+    R1_CUDA(cudaMemsetAsync(d_num_rays, 0, sizeof(unsigned long long), stream));
+    R1_CUDA(cudaEventRecord(c.ev[0], stream));
+    if (a.npix_local > 0) {
+        rc = grow(c.partial, c.partial_cap, (size_t)a.n_units);
+        if (rc) return rc;
+        a.partial = c.partial;
+        R1_CUDA(cudaMemsetAsync(c.unit_counter, 0, sizeof(unsigned int), stream));
+        const bool staged = c.dev.n_pad <= r1::kMaxStagedSpheres;
+        R1_CUDA(cudaEventRecord(c.ev[1], stream));
+        if (prm.variant == R1_VARIANT_WAVEFRONT) {
+            uint32_t launches = 0;
+            rc = r1::wavefront_render(c.wf, a, c.sm_count, stream, &launches);
+            if (rc) return fail(R1_ERR_CUDA, "wavefront: %s", cudaGetErrorString((cudaError_t)rc));
+            c.last_launches += launches;
+        } else {
+            const bool packed = prm.variant == R1_VARIANT_MEGAKERNEL;
+            if (packed && staged) rc = launch_megakernel<true, true>(c, a, prm, stream);
+            else if (packed) rc = launch_megakernel<true, false>(c, a, prm, stream);
+            else if (staged) rc = launch_megakernel<false, true>(c, a, prm, stream);
+            else rc = launch_megakernel<false, false>(c, a, prm, stream);
+            if (rc) return rc;
+            c.last_launches += 1;
+        }
+        R1_CUDA(cudaEventRecord(c.ev[2], stream));
+        const int rgrid = (int)std::min<uint64_t>(((uint64_t)a.npix_local + 255) / 256, (uint64_t)c.sm_count * 8);
+        r1::resolve<<<rgrid, 256, 0, stream>>>(a);
+        R1_CUDA(cudaGetLastError());
+        c.last_launches += 1;
+    } else {
+        R1_CUDA(cudaEventRecord(c.ev[1], stream));
+        R1_CUDA(cudaEventRecord(c.ev[2], stream));
+    }
+    R1_CUDA(cudaEventRecord(c.ev[3], stream));
+    if (result) {
+        memset(result, 0, sizeof(*result));
+        result->num_samples = c.last_samples;
+        result->launches = c.last_launches;
+        result->n_units = c.last_units;
+    }
+    return R1_OK;
+}
+
+int r1_render_wait(r1_scene *scene, int device, r1_result *result)
+{
+    DeviceCtx *cp = nullptr;
+    int rc = get_ctx(scene, &cp, device);
+    if (rc) return rc;
+    DeviceCtx &c = *cp;
+    R1_CUDA(cudaEventSynchronize(c.ev[3]));
+    if (result) {
+        float ms_all = 0, ms_trace = 0;
+        R1_CUDA(cudaEventElapsedTime(&ms_all, c.ev[0], c.ev[3]));
+        R1_CUDA(cudaEventElapsedTime(&ms_trace, c.ev[1], c.ev[2]));
+        result->kernel_ms = ms_all;
+        result->trace_ms = ms_trace;
+        result->num_samples = c.last_samples;
+        result->launches = c.last_launches;
+        result->n_units = c.last_units;
+    }
+    return R1_OK;
+}
+
+int r1_render(r1_scene *scene, const r1_render_params *params, uint8_t *rgb_host, r1_result *result)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = validate(params);
+    if (rc) return rc;
+    if (!rgb_host) return fail(R1_ERR_ARG, "null rgb_host");
+    DeviceCtx *cp = nullptr;
+    rc = get_ctx(scene, &cp, params->device);
+    if (rc) return rc;
+    DeviceCtx &c = *cp;
+    const Partition part = partition(params->width, params->height, params->row_tile, params->rank, params->world);
+    const size_t bytes = (size_t)part.npix_local * 3;
+    rc = grow(c.rgb, c.rgb_cap, std::max<size_t>(bytes, 16));
+    if (rc) return rc;
+    r1_result res;
+    rc = r1_render_device(scene, params, c.rgb, c.num_rays, nullptr, &res);
+    if (rc) return rc;
+    unsigned long long rays = 0;
+    if (bytes) R1_CUDA(cudaMemcpyAsync(rgb_host, c.rgb, bytes, cudaMemcpyDeviceToHost, nullptr));
+    R1_CUDA(cudaMemcpyAsync(&rays, c.num_rays, sizeof(rays), cudaMemcpyDeviceToHost, nullptr));
+    R1_CUDA(cudaStreamSynchronize(nullptr));
+    rc = r1_render_wait(scene, params->device, &res);
+    if (rc) return rc;
+    res.num_rays = rays;
+    res.elapsed_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (result) *result = res;
+    return R1_OK;
+}
+
+}  // extern "C"
+
+// ---- parity entry points -------------------------------------------------------------------------------------
+
+namespace {
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) { R1_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 16))); return R1_OK; }
+    int upload(const void *src, size_t bytes) { int rc = alloc(bytes); if (rc) return rc; R1_CUDA(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice)); return R1_OK; }
+    int download(void *dst, size_t bytes) { R1_CUDA(cudaMemcpy(dst, p, bytes, cudaMemcpyDeviceToHost)); return R1_OK; }
+    template <typename T> T *as() { return reinterpret_cast<T *>(p); }
+};
+#define R1_TRY(expr) do { int rc_ = (expr); if (rc_) return rc_; } while (0)
+}  // namespace
+
+extern "C" {
+
+int r1_trace_rays(r1_scene *scene, int n, const float *org, const float *dir, float t_min, float t_max, int variant, int32_t *index, float *t,
+                  float *p, float *normal)
+{
+    DeviceCtx *cp = nullptr;
+    R1_TRY(get_ctx(scene, &cp));
+    if (n < 0 || (n > 0 && (!org || !dir || !index || !t || !p || !normal))) return fail(R1_ERR_ARG, "bad argument");
+    if (n == 0) return R1_OK;
+    if (cp->dev.n_pad > r1::kMaxStagedSpheres) return fail(R1_ERR_LIMIT, "r1_trace_rays stages at most %d spheres", r1::kMaxStagedSpheres);
+    DevBuf d_org, d_dir, d_idx, d_t, d_p, d_n;
+    R1_TRY(d_org.upload(org, (size_t)n * 12)); R1_TRY(d_dir.upload(dir, (size_t)n * 12));
+    R1_TRY(d_idx.alloc((size_t)n * 4)); R1_TRY(d_t.alloc((size_t)n * 4)); R1_TRY(d_p.alloc((size_t)n * 12)); R1_TRY(d_n.alloc((size_t)n * 12));
+    const size_t smem = 16 + (size_t)cp->dev.n_pad * 32;
+    const int grid = (n + 127) / 128;
+    if (variant == R1_VARIANT_MEGAKERNEL_SCALAR) {
+        R1_CUDA(cudaFuncSetAttribute(r1::trace_rays_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        r1::trace_rays_kernel<false><<<grid, 128, smem>>>(cp->dev, n, d_org.as<float>(), d_dir.as<float>(), t_min, t_max, d_idx.as<int32_t>(),
+                                                          d_t.as<float>(), d_p.as<float>(), d_n.as<float>());
+    } else {
+        R1_CUDA(cudaFuncSetAttribute(r1::trace_rays_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        r1::trace_rays_kernel<true><<<grid, 128, smem>>>(cp->dev, n, d_org.as<float>(), d_dir.as<float>(), t_min, t_max, d_idx.as<int32_t>(),
+                                                         d_t.as<float>(), d_p.as<float>(), d_n.as<float>());
+    }
+    R1_CUDA(cudaGetLastError());
+    R1_CUDA(cudaDeviceSynchronize());
+    R1_TRY(d_idx.download(index, (size_t)n * 4)); R1_TRY(d_t.download(t, (size_t)n * 4));
+    R1_TRY(d_p.download(p, (size_t)n * 12)); R1_TRY(d_n.download(normal, (size_t)n * 12));
+    return R1_OK;
+}
+
+int r1_scatter(r1_scene *scene, int n, const float *dir_in, const float *p, const float *normal, const int32_t *index, const float *rand_sphere,
+               const float *rand_u, int32_t *ok, float *atten, float *dir_out)
+{
+    DeviceCtx *cp = nullptr;
+    R1_TRY(get_ctx(scene, &cp));
+    if (n < 0 || (n > 0 && (!dir_in || !p || !normal || !index || !rand_sphere || !rand_u || !ok || !atten || !dir_out))) return fail(R1_ERR_ARG, "bad argument");
+    if (n == 0) return R1_OK;
+    DevBuf a, b, c, d, e, f, g, h, i;
+    R1_TRY(a.upload(dir_in, (size_t)n * 12)); R1_TRY(b.upload(p, (size_t)n * 12)); R1_TRY(c.upload(normal, (size_t)n * 12));
+    R1_TRY(d.upload(index, (size_t)n * 4)); R1_TRY(e.upload(rand_sphere, (size_t)n * 12)); R1_TRY(f.upload(rand_u, (size_t)n * 4));
+    R1_TRY(g.alloc((size_t)n * 4)); R1_TRY(h.alloc((size_t)n * 12)); R1_TRY(i.alloc((size_t)n * 12));
+    r1::scatter_kernel<<<(n + 127) / 128, 128>>>(cp->dev, n, a.as<float>(), b.as<float>(), c.as<float>(), d.as<int32_t>(), e.as<float>(), f.as<float>(),
+                                                 g.as<int32_t>(), h.as<float>(), i.as<float>());
+    R1_CUDA(cudaGetLastError());
+    R1_CUDA(cudaDeviceSynchronize());
+    R1_TRY(g.download(ok, (size_t)n * 4)); R1_TRY(h.download(atten, (size_t)n * 12)); R1_TRY(i.download(dir_out, (size_t)n * 12));
+    return R1_OK;
+}
+
+int r1_get_ray(r1_scene *scene, int n, const float *su, const float *tv, const float *disk, float *org, float *dir)
+{
+    DeviceCtx *cp = nullptr;
+    R1_TRY(get_ctx(scene, &cp));
+    if (n < 0 || (n > 0 && (!su || !tv || !disk || !org || !dir))) return fail(R1_ERR_ARG, "bad argument");
+    if (n == 0) return R1_OK;
+    DevBuf a, b, c, d, e;
+    R1_TRY(a.upload(su, (size_t)n * 4)); R1_TRY(b.upload(tv, (size_t)n * 4)); R1_TRY(c.upload(disk, (size_t)n * 8));
+    R1_TRY(d.alloc((size_t)n * 12)); R1_TRY(e.alloc((size_t)n * 12));
+    r1::get_ray_kernel<<<(n + 127) / 128, 128>>>(cp->dev, n, a.as<float>(), b.as<float>(), c.as<float>(), d.as<float>(), e.as<float>());
+    R1_CUDA(cudaGetLastError());
+    R1_CUDA(cudaDeviceSynchronize());
+    R1_TRY(d.download(org, (size_t)n * 12)); R1_TRY(e.download(dir, (size_t)n * 12));
+    return R1_OK;
+}
+
+int r1_rng_draws(uint32_t pixel, uint32_t sample, uint32_t seed, int n, uint32_t *out)
+{
+    if (n < 0 || (n > 0 && !out)) return fail(R1_ERR_ARG, "bad argument");
+    if (n == 0) return R1_OK;
+    DevBuf d;
+    R1_TRY(d.alloc((size_t)n * 4));
+    r1::rng_kernel<<<1, 32>>>(pixel, sample, seed, n, d.as<uint32_t>());
+    R1_CUDA(cudaGetLastError());
+    R1_CUDA(cudaDeviceSynchronize());
+    R1_TRY(d.download(out, (size_t)n * 4));
+    return R1_OK;
+}
+
+int r1_fma_peak(int device, int packed, double *tflops, double *sm_mhz_est)
+{
+    if (!tflops) return fail(R1_ERR_ARG, "null argument");
+    R1_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    R1_CUDA(cudaGetDeviceProperties(&prop, device));
+    DevBuf sink, cyc;
+    R1_TRY(sink.alloc(16)); R1_TRY(cyc.alloc(16));
+    const int iters = 1 << 16, threads = 256, grid = prop.multiProcessorCount * 8;
+    cudaEvent_t e0, e1;
+    R1_CUDA(cudaEventCreate(&e0)); R1_CUDA(cudaEventCreate(&e1));
+    double best_ms = 1e30;
+    for (int rep = 0; rep < 4; ++rep) {  // first repetition is the warm-up
+        R1_CUDA(cudaEventRecord(e0));
+        if (packed) r1::fma_peak_kernel<true><<<grid, threads>>>(iters, 0.5f, sink.as<float>(), cyc.as<long long>());
+        else r1::fma_peak_kernel<false><<<grid, threads>>>(iters, 0.5f, sink.as<float>(), cyc.as<long long>());
+        R1_CUDA(cudaEventRecord(e1));
+        R1_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        R1_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best_ms) best_ms = ms;
+    }
+    long long cycles = 0;
+    R1_TRY(cyc.download(&cycles, sizeof(cycles)));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    const double fmas = (double)grid * threads * (double)iters * 16.0;  // 16 scalar FMAs or 8 packed (= 16) per iteration
+    *tflops = 2.0 * fmas / (best_ms * 1e-3) / 1e12;
+    // one CTA's cycle count spans ~1/waves of the kernel: grid = 8 CTAs/SM of 256 threads all resident -> one wave
+    if (sm_mhz_est) *sm_mhz_est = (double)cycles / (best_ms * 1e-3) / 1e6;
+    return R1_OK;
+}
+
+}  // extern "C"

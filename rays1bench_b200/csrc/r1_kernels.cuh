@@ -1,0 +1,304 @@
+// r1_kernels.cuh -- sm_100a kernels of the Rays1 trace loop: persistent-thread megakernel, framebuffer resolve,
+// parity kernels and the FP32 FMA peak microbenchmark.  (The wavefront variant lives in r1_wavefront.cuh.)
+// file:line citations are relative to /root/reference/.
+#pragma once
+#include "r1_device.cuh"
+
+namespace r1 {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+// Work decomposition: unit u = (sample chunk c, local pixel lp), u = c * npix_local + lp.  A unit is `samples_per_unit`
+// consecutive samples of one pixel, summed in order by one lane and written to partial[u]; resolve() adds a pixel's
+// chunks in ascending c.  samples_per_unit depends on spp only, so the float summation tree -- and therefore the RGB8
+// image -- is identical for every GPU count, block shape and kernel variant.
+struct RenderArgs {
+    DevScene scene;
+    float4 *partial;                 // n_units
+    unsigned long long *num_rays;    // += one per traced ray (rayweek1.cpp:517)
+    unsigned int *unit_counter;      // next unit to hand out
+    uint8_t *rgb;                    // npix_local * 3, local rows packed, row 0 = bottom
+    int32_t width, height, spp, max_bounces;
+    int32_t rank, world, row_tile;
+    uint32_t npix_local, n_units;
+    int32_t samples_per_unit, n_chunks;
+    uint32_t seed;
+    float inv_w, inv_h, inv_spp;
+};
+
+// ------------------------------------------------------------------------------------------------ TMA staging
+// One 1-D bulk copy (cp.async.bulk -> UBLKCP) brings [scan | exact] = n_pad * 32 bytes into shared memory; an
+// mbarrier with a transaction count signals arrival.  Every CTA reads the same <= 128 KB, which stays L2-resident.
+__device__ __forceinline__ void stage_spheres(const DevScene &sc, float4 *s_spheres, uint64_t *bar)
+{
+    const uint32_t bytes = (uint32_t)sc.n_pad * 32u;
+    const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(s_spheres)),
+                     "l"(sc.scan), "r"(bytes), "r"(bar_s)
+                     : "memory");
+    }
+    __syncthreads();  // barrier initialised before anyone polls it
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done)
+                     : "r"(bar_s)
+                     : "memory");
+    }
+}
+
+// y of local row lr under the interleaved row-tile partition (tile k -> rank k % world)
+__device__ __host__ __forceinline__ int global_row(int lr, int row_tile, int rank, int world)
+{
+    return ((lr / row_tile) * world + rank) * row_tile + (lr % row_tile);
+}
+
+// ------------------------------------------------------------------------------------------------ megakernel
+// Persistent CTAs; every lane runs  loop { take a unit | start a sample | SCAN | shade }  so that all 32 lanes enter
+// every scan with a live ray and divergence is confined to the short fetch / generate / shade steps.
+// Replaces render_tile + color + TileRenderScheduler (rayweek1.cpp:722-842, 515-536).
+template <bool kPacked, bool kStaged, int kThreads, int kBlocksPerSM>
+__global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel(const __grid_constant__ RenderArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const float4 *s_scan, *s_exact;
+    if (kStaged) {
+        float4 *s_spheres = reinterpret_cast<float4 *>(smem_raw + 16);
+        stage_spheres(a.scene, s_spheres, reinterpret_cast<uint64_t *>(smem_raw));
+        s_scan = s_spheres;
+        s_exact = s_spheres + a.scene.n_pad;
+    } else {  // scenes beyond the staging limit scan straight from global memory (L1/L2 resident)
+        s_scan = a.scene.scan;
+        s_exact = a.scene.exact;
+    }
+    const int n_pad = a.scene.n_pad;
+    const unsigned lane = threadIdx.x & 31u;
+
+    bool active = false, exhausted = false, need_primary = false;
+    uint32_t unit = 0, pixel = 0, nrays = 0;
+    int s = 0, s_end = 0, depth = 0;
+    float fx = 0.0f, fy = 0.0f;
+    f3 acc = mk3(0, 0, 0), thr = mk3(1, 1, 1);
+    f3 o = mk3(0.0f, 1.0e18f, 0.0f), d = mk3(0.0f, 0.0f, 0.0f);  // idle lanes scan a ray that passes no filter
+    Rng rng;
+    rng.key = 0; rng.ctr = 0;
+
+    for (;;) {
+        // -- take a unit (warp-aggregated: one atomic per warp per refill round)
+        const bool want = !active && !exhausted;
+        const unsigned need = __ballot_sync(kFull, want);
+        if (need) {
+            const int leader = __ffs(need) - 1;
+            unsigned base = 0;
+            if ((int)lane == leader) base = atomicAdd(a.unit_counter, (unsigned)__popc(need));
+            base = __shfl_sync(kFull, base, leader);
+            if (want) {
+                unit = base + __popc(need & ((1u << lane) - 1u));
+                if (unit < a.n_units) {
+                    const uint32_t c = unit / a.npix_local, lp = unit - c * a.npix_local;
+                    const int lr = (int)(lp / (uint32_t)a.width), x = (int)(lp - (uint32_t)lr * (uint32_t)a.width);
+                    const int y = global_row(lr, a.row_tile, a.rank, a.world);
+                    pixel = (uint32_t)y * (uint32_t)a.width + (uint32_t)x;
+                    fx = (float)x; fy = (float)y;
+                    s = (int)c * a.samples_per_unit;
+                    s_end = min(s + a.samples_per_unit, a.spp);
+                    acc = mk3(0, 0, 0);
+                    active = true; need_primary = true;
+                } else {
+                    exhausted = true;
+                    o = mk3(0.0f, 1.0e18f, 0.0f); d = mk3(0.0f, 0.0f, 0.0f);
+                }
+            }
+        }
+        if (__all_sync(kFull, exhausted)) break;
+
+        // -- start a sample: jitter (rayweek1.cpp:759), lens disk + camera ray (:760, :381-386)
+        if (active && need_primary) {
+            rng.seed(pixel, (uint32_t)s, a.seed);
+            const float u = fmul(fadd(rng.rand01(), fx), a.inv_w), v = fmul(fadd(rng.rand01(), fy), a.inv_h);
+            float px, py;
+            random_in_unit_disk(rng, px, py);
+            camera_ray(a.scene.cam, u, v, px, py, o, d);
+            thr = mk3(1, 1, 1);
+            depth = 0;
+            need_primary = false;
+        }
+
+        // -- Hitable::hit (rayweek1.cpp:152-339): uniform trip count, all lanes
+        float t = kTMax;
+        int hit = -1;
+        scan<kPacked>(s_scan, s_exact, n_pad, o, d, kTMin, t, hit);
+
+        // -- color() body (rayweek1.cpp:515-536)
+        if (active) {
+            ++nrays;
+            bool done = true;
+            f3 contrib = mk3(0, 0, 0);
+            if (hit < 0) {
+                const f3 sk = sky(d);
+                contrib = mk3(fmul(thr.x, sk.x), fmul(thr.y, sk.y), fmul(thr.z, sk.z));
+            } else if (depth < a.max_bounces) {
+                f3 p, n, atten, nd, rs = mk3(0, 0, 0);
+                float ru = 0.0f;
+                hit_finalise(s_exact[hit], __ldg(a.scene.inv_radius + hit), o, d, t, p, n);
+                const int kind = __ldg(a.scene.kind + hit);
+                const float4 mat = __ldg(a.scene.mat + hit);
+                if (kind == 2) ru = rng.rand01();
+                else rs = random_in_unit_sphere(rng);
+                if (scatter(kind, mat, d, p, n, rs, ru, atten, nd)) {
+                    thr = mk3(fmul(thr.x, atten.x), fmul(thr.y, atten.y), fmul(thr.z, atten.z));
+                    o = p; d = nd; ++depth;
+                    done = false;
+                }
+            }
+            if (done) {
+                acc = add3(acc, contrib);
+                if (++s == s_end) {
+                    a.partial[unit] = make_float4(acc.x, acc.y, acc.z, 0.0f);
+                    active = false;
+                    o = mk3(0.0f, 1.0e18f, 0.0f); d = mk3(0.0f, 0.0f, 0.0f);
+                } else {
+                    need_primary = true;
+                }
+            }
+        }
+    }
+    // -- total-rays counter (rayweek1.cpp:809-813): warp reduce, one 64-bit atomic per warp
+    unsigned long long total = nrays;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(kFull, total, off);
+    if (lane == 0 && total) atomicAdd(a.num_rays, total);
+}
+
+// ------------------------------------------------------------------------------------------------ resolve
+// rayweek1.cpp:765-775: average, gamma 2 (sqrtf), quantise (int)(c * 255.99f) -> RGB8.
+__device__ __forceinline__ uint8_t quantise(float sum, float inv_spp)
+{
+    const float c = __fsqrt_rn(fmul(sum, inv_spp));
+    return (uint8_t)(int)fmul(c, 255.99f);
+}
+__global__ void __launch_bounds__(256) resolve(const __grid_constant__ RenderArgs a)
+{
+    for (uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x; lp < a.npix_local; lp += gridDim.x * blockDim.x) {
+        float r = 0.0f, g = 0.0f, b = 0.0f;
+        for (int c = 0; c < a.n_chunks; ++c) {
+            const float4 v = a.partial[(size_t)c * a.npix_local + lp];
+            r = fadd(r, v.x); g = fadd(g, v.y); b = fadd(b, v.z);
+        }
+        uint8_t *out = a.rgb + (size_t)lp * 3;
+        out[0] = quantise(r, a.inv_spp); out[1] = quantise(g, a.inv_spp); out[2] = quantise(b, a.inv_spp);
+    }
+}
+
+// Multi-GPU epilogue: slice r of `gathered` = rank r's local rows; scatter them to their global rows.
+__global__ void __launch_bounds__(256) deinterleave_rows(const uint8_t *gathered, size_t stride, uint8_t *out, int width, int height, int row_tile, int world)
+{
+    const size_t row_bytes = (size_t)width * 3, total = row_bytes * (size_t)height;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int y = (int)(i / row_bytes);
+        const size_t xb = i - (size_t)y * row_bytes;
+        const int tile = y / row_tile, rank = tile % world;
+        const int lr = (tile / world) * row_tile + (y - tile * row_tile);
+        out[i] = gathered[(size_t)rank * stride + (size_t)lr * row_bytes + xb];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ parity kernels
+template <bool kPacked>
+__global__ void __launch_bounds__(128) trace_rays_kernel(const __grid_constant__ DevScene sc, int n, const float *org, const float *dir,
+                                                         float t_min, float t_max, int32_t *index, float *t_out, float *p_out, float *n_out)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4 *s_spheres = reinterpret_cast<float4 *>(smem_raw + 16);
+    stage_spheres(sc, s_spheres, reinterpret_cast<uint64_t *>(smem_raw));
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const f3 o = mk3(org[3 * k], org[3 * k + 1], org[3 * k + 2]), d = mk3(dir[3 * k], dir[3 * k + 1], dir[3 * k + 2]);
+    float t = t_max;
+    int hit = -1;
+    scan<kPacked>(s_spheres, s_spheres + sc.n_pad, sc.n_pad, o, d, t_min, t, hit);
+    f3 p = mk3(0, 0, 0), nrm = mk3(0, 0, 0);
+    if (hit >= 0) hit_finalise(s_spheres[sc.n_pad + hit], sc.inv_radius[hit], o, d, t, p, nrm);
+    index[k] = hit;
+    t_out[k] = hit >= 0 ? t : 0.0f;
+    p_out[3 * k] = p.x; p_out[3 * k + 1] = p.y; p_out[3 * k + 2] = p.z;
+    n_out[3 * k] = nrm.x; n_out[3 * k + 1] = nrm.y; n_out[3 * k + 2] = nrm.z;
+}
+
+__global__ void scatter_kernel(const __grid_constant__ DevScene sc, int n, const float *dir_in, const float *p, const float *nrm,
+                               const int32_t *index, const float *rs, const float *ru, int32_t *ok, float *atten, float *dir_out)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int i = index[k];
+    f3 a = mk3(0, 0, 0), dd = mk3(0, 0, 0);
+    bool r = false;
+    if (i >= 0 && i < sc.n_pad && sc.kind[i] >= 0)
+        r = scatter(sc.kind[i], sc.mat[i], mk3(dir_in[3 * k], dir_in[3 * k + 1], dir_in[3 * k + 2]), mk3(p[3 * k], p[3 * k + 1], p[3 * k + 2]),
+                    mk3(nrm[3 * k], nrm[3 * k + 1], nrm[3 * k + 2]), mk3(rs[3 * k], rs[3 * k + 1], rs[3 * k + 2]), ru[k], a, dd);
+    ok[k] = r ? 1 : 0;
+    atten[3 * k] = a.x; atten[3 * k + 1] = a.y; atten[3 * k + 2] = a.z;
+    dir_out[3 * k] = dd.x; dir_out[3 * k + 1] = dd.y; dir_out[3 * k + 2] = dd.z;
+}
+
+__global__ void get_ray_kernel(const __grid_constant__ DevScene sc, int n, const float *su, const float *tv, const float *disk, float *org, float *dir)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    f3 o, d;
+    camera_ray(sc.cam, su[k], tv[k], disk[2 * k], disk[2 * k + 1], o, d);
+    org[3 * k] = o.x; org[3 * k + 1] = o.y; org[3 * k + 2] = o.z;
+    dir[3 * k] = d.x; dir[3 * k + 1] = d.y; dir[3 * k + 2] = d.z;
+}
+
+__global__ void rng_kernel(uint32_t pixel, uint32_t sample, uint32_t seed, int n, uint32_t *out)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        Rng rng;
+        rng.seed(pixel, sample, seed);
+        for (int i = 0; i < n; ++i) out[i] = rng.next();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ FP32 peak
+// 16 independent accumulator chains per thread; packed = FFMA2 on float2 accumulators.  FLOPs = 2 per FMA.
+template <bool kPacked>
+__global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float seed, float *sink, long long *cycles)
+{
+    const long long c0 = clock64();
+    float r = 0.0f;
+    if (kPacked) {
+        float2 acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = make_float2(seed + k, seed - k);
+        const float2 m = make_float2(1.0000001f, 0.9999999f), b = make_float2(seed, -seed);
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = __ffma2_rn(acc[k], m, b);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r += acc[k].x + acc[k].y;
+    } else {
+        float acc[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc[k] = seed + k;
+        const float m = 1.0000001f, b = seed;
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) acc[k] = ffma(acc[k], m, b);
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) r += acc[k];
+    }
+    const long long c1 = clock64();
+    if (r == 123.456f) sink[0] = r;  // keep the chains alive
+    if (blockIdx.x == 0 && threadIdx.x == 0) cycles[0] = c1 - c0;
+}
+
+}  // namespace r1

@@ -1,0 +1,208 @@
+"""CPU-side checks of the C-ABI library and the host logic: the library loads and exports every symbol the header
+declares, the scene builders produce the reference's SoA arrays bit for bit, the row-tile partition is a partition,
+compute entry points fail loudly without a GPU, TGA / log files have the reference's format, and the two-collective
+exchange works at world_size 2 over gloo.  No kernels run here."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, SCENES
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def test_library_exports_every_declared_symbol(r1):
+    header = open(os.path.join(ROOT, "include", "rays1_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(r1_\w+)\s*\(", header))
+    assert len(declared) >= 30
+    nm = subprocess.run(["nm", "-D", "--defined-only", r1.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\sT\s+(r1_\w+)", nm))
+    assert declared <= exported, sorted(declared - exported)
+    assert declared == set(r1.EXPORTED), sorted(declared ^ set(r1.EXPORTED))
+    assert r1.lib.r1_abi_version() == 1
+
+
+def test_library_is_built_for_sm100a_only(r1):
+    out = subprocess.run(["cuobjdump", "-lelf", r1.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\w+)\.", out))
+    assert archs == {"100a"}, archs
+
+
+def test_product_does_not_link_or_reference_the_oracle(r1):
+    """the oracle is test infrastructure: nothing under rays1bench_b200/ may name it"""
+    pkg = os.path.join(ROOT, "rays1bench_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "rays1_oracle" not in text and "cpu_checkers" not in text and "oracle/" not in text, f
+    ldd = subprocess.run(["ldd", r1.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in ldd and "libref" not in ldd
+
+
+@pytest.mark.parametrize("name", SCENES + ("synth4096",))
+def test_scene_builders_match_oracle_bit_for_bit(r1, oracle, name):
+    s = r1.create_scene(name, commit=False)
+    so = oracle.scene_create(name)
+    a, b = s.soa(), oracle.scene_soa(so)
+    assert s.count() == oracle.scene_count(so) == {"small": 8, "medium": 48, "large": 488, "synth4096": 4096}[name]
+    for k in a:
+        assert np.array_equal(a[k], b[k]) if a[k].dtype != np.float32 else np.array_equal(bits(a[k]), bits(b[k])), k
+    np.testing.assert_allclose(s.camera(), oracle.scene_camera(so), rtol=1e-6, atol=4e-6)
+    oracle.scene_destroy(so)
+    s.close()
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_scene_builders_match_reference_golden(r1, golden_rays, name):
+    s = r1.create_scene(name, commit=False)
+    a, g = s.soa(), golden_rays[name]
+    for k in ("cx", "cy", "cz", "radius_sq", "inv_radius"):
+        assert np.array_equal(bits(a[k]), bits(g["soa_" + k])), k
+    assert np.array_equal(a["kind"], g["soa_kind"])
+    np.testing.assert_allclose(a["albedo"], g["soa_albedo"], rtol=2e-7, atol=1e-9)
+    np.testing.assert_allclose(a["param"], g["soa_param"], rtol=2e-7)
+    np.testing.assert_allclose(s.camera(), g["camera"], rtol=1e-6, atol=4e-6)
+    # placeholders: radius 0 at 999999999, no material (rayweek1.cpp:575-576); the hollow shell keeps inv_radius 0
+    ph = a["kind"] == r1.MAT_NONE
+    assert (a["cx"][ph] == np.float32(999999999)).all() and (a["inv_radius"][ph] == 0).all()
+    if name == "small":
+        assert a["inv_radius"][4] == 0 and a["radius_sq"][4] == np.float32(-0.45) * np.float32(-0.45)
+    s.close()
+
+
+def test_scene_abi_argument_checking(r1):
+    import ctypes as C
+    lib = r1.lib
+    sc = lib.r1_scene_create(4)
+    assert lib.r1_scene_add_sphere(sc, 0, 0, 0, 1.0, 7, 0, 0, 0, 0) == -1      # unknown material
+    assert lib.r1_scene_add_sphere(sc, 0, 0, 0, 1.0, r1.MAT_NONE, 0, 0, 0, 0) == -1  # real sphere needs a material
+    assert lib.r1_scene_add_sphere(sc, 0, 0, 0, 1.0, r1.MAT_METAL, .5, .5, .5, 3.0) == 0
+    assert lib.r1_scene_pad(sc, 8) == 0 and lib.r1_scene_count(sc) == 8
+    n = 8
+    arr = lambda k=1: np.zeros(n * k, np.float32)  # noqa: E731
+    cx, cy, cz, r2, ir, al, pa, kind = arr(), arr(), arr(), arr(), arr(), arr(3), arr(), np.zeros(n, np.int32)
+    assert lib.r1_scene_get_soa(sc, cx, cy, cz, r2, ir, kind, al, pa) == 0
+    assert pa[0] == 1.0, "Metal fuzz is clamped to <= 1 (rayweek1.cpp:424)"
+    assert lib.r1_scene_commit(sc, 0) == -2 and b"camera" in lib.r1_last_error()  # camera not set
+    p = r1.RenderParams(16, 9, 1, 50, 0, 0, 0, 1, 8, 0, -1)
+    res = r1.Result()
+    assert lib.r1_render(sc, C.byref(p), np.zeros(16 * 9 * 3, np.uint8), C.byref(res)) == -2  # not committed
+    p.world = 0
+    assert lib.r1_render(sc, C.byref(p), np.zeros(16 * 9 * 3, np.uint8), C.byref(res)) == -1
+    lib.r1_scene_destroy(sc)
+
+
+def test_no_cpu_fallback_without_a_gpu(r1):
+    """On a box without a CUDA device every compute entry point must fail loudly (never render on the CPU)."""
+    try:
+        n = r1.device_count()
+    except r1.Rays1Error:
+        n = 0
+    if n > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(r1.Rays1Error):
+        r1.create_large_scene()
+    with pytest.raises(r1.Rays1Error):
+        r1.fma_peak()
+    s = r1.create_scene("small", commit=False)
+    with pytest.raises(r1.Rays1Error):
+        s.render(16, 9, 1)
+    with pytest.raises(r1.Rays1Error):
+        s.trace_rays(np.zeros((1, 3)), np.array([[0, 0, 1.0]]))
+    s.close()
+
+
+@pytest.mark.parametrize("height,row_tile,world", [(720, 8, 1), (720, 8, 2), (720, 8, 8), (2160, 8, 8), (37, 8, 4), (5, 8, 8), (100, 3, 7)])
+def test_row_tile_partition_is_a_partition(r1, height, row_tile, world):
+    seen = []
+    for rank in range(world):
+        rows = r1.local_rows(height, row_tile, rank, world)
+        ys = [r1.global_row(lr, row_tile, rank, world) for lr in range(rows)]
+        assert ys == sorted(ys), "local rows are in ascending global order"
+        assert all((y // row_tile) % world == rank for y in ys)
+        seen += ys
+    assert sorted(seen) == list(range(height))
+    counts = [r1.local_rows(height, row_tile, r, world) for r in range(world)]
+    assert max(counts) - min(counts) <= row_tile
+
+
+def test_tga_writer_format(r1, tmp_path):
+    """common.h:86-122: 18-byte header, type 2, 24 bpp, descriptor 0, BGR payload, and R/B swapped IN PLACE."""
+    w, h = 5, 3
+    px = np.arange(w * h * 3, dtype=np.uint8).reshape(h, w, 3)
+    orig = px.copy()
+    path = str(tmp_path / "out_x.tga")
+    r1.tga_write_rgb24(path, w, h, px)
+    raw = open(path, "rb").read()
+    assert len(raw) == 18 + w * h * 3
+    assert list(raw[:18]) == [0, 0, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, w, 0, h, 0, 24, 0]
+    body = np.frombuffer(raw[18:], np.uint8).reshape(h, w, 3)
+    assert np.array_equal(body, orig[:, :, ::-1])
+    assert np.array_equal(px, orig[:, :, ::-1]), "the caller's buffer is swapped too, as in the reference"
+
+
+def test_log_results_format(r1, tmp_path, monkeypatch):
+    """common.h:47-77 -> 'version|%.3fs|<rays>|%0.3f mrays/s|' (no newline), averaged; parsed by update_readme.py:30-31"""
+    monkeypatch.chdir(tmp_path)
+    a, b = r1.Result(), r1.Result()
+    a.elapsed_seconds, a.num_rays = 2.0, 100_000_000
+    b.elapsed_seconds, b.num_rays = 4.0, 300_000_000
+    r1.log_results("b200", "large", [a, b])
+    txt = open(tmp_path / "out_large.txt").read()
+    assert txt == "b200|3.000s|200000000|66.667 mrays/s|"
+    tokens = txt.split("|")
+    assert float(tokens[3].split()[0]) == pytest.approx(66.667)
+
+
+def test_flops_model(r1):
+    # F_ray = 16 N + 70 -> small 150, medium 806, large 7814, synthetic 65606
+    assert [r1.flops_per_ray(r1.REAL_SPHERES[k]) for k in ("small", "medium", "large", "synth4096")] == [150, 806, 7814, 65606]
+
+
+GLOO_WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+import rays1bench_b200 as r1
+from rays1bench_b200 import dist as r1d
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+W, H, T = 13, 37, 4
+rows = r1.local_rows(H, T, rank, world)
+mx = r1d.max_local_rows(H, T, world)
+local = torch.zeros((mx, W, 3), dtype=torch.uint8)
+for lr in range(rows):
+    y = r1.global_row(lr, T, rank, world)
+    local[lr] = torch.tensor([(y * 7 + x * 3 + c) % 256 for x in range(W) for c in range(3)], dtype=torch.uint8).reshape(W, 3)
+gathered = r1d.gather_framebuffer(local, H, T, rank, world)
+count = r1d.reduce_ray_count(torch.tensor([1000 + rank], dtype=torch.int64), world)
+if rank == 0:
+    parts = [gathered[r, : r1.local_rows(H, T, r, world)].numpy() for r in range(world)]
+    img = r1.assemble_rows(parts, H, T)
+    want = np.array([[[(y * 7 + x * 3 + c) % 256 for c in range(3)] for x in range(W)] for y in range(H)], np.uint8)
+    assert np.array_equal(img, want)
+    assert int(count) == sum(1000 + r for r in range(world)), int(count)
+    print("GLOO_OK")
+else:
+    assert gathered is None
+dist.destroy_process_group()
+"""
+
+
+def test_two_collective_exchange_world2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29641", str(script), ROOT]
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "GLOO_OK" in out.stdout

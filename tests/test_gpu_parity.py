@@ -1,0 +1,287 @@
+"""Parity of the CUDA path (through the C ABI) against the reference: golden vectors recorded from the reference's
+compiled code, the oracle on fresh seeded inputs, and size-independent properties at the full BASELINE.json sizes.
+Tolerances: hit index exact; t / p / normal / scatter direction within 1e-5 (north_star; in practice hit results are
+bit-identical because the exact candidate path uses the reference's as-built arithmetic); rays per sample within 0.5 %;
+per-channel image RMSE vs the reference's 16384-spp render <= 1/255."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import SCENES, rmse
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def scenes(r1):
+    r1.configure(width=1280, height=720, spp=250, max_bounces=50, variant=0, n_gpus=1, seed=0, quiet=True)
+    out = {name: r1.create_scene(name) for name in SCENES + ("synth4096",)}
+    yield out
+    for s in out.values():
+        s.close()
+
+
+# ---- hit() ----------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("variant", ["mega", "scalar"])
+@pytest.mark.parametrize("name", SCENES)
+def test_hit_matches_reference_golden(r1, scenes, golden_rays, name, variant):
+    g = golden_rays[name]
+    org = np.concatenate([g["seg_org"], g["edge_org"]])
+    d = np.concatenate([g["seg_dir"], g["edge_dir"]])
+    want_idx = np.concatenate([g["seg_index"], g["edge_index"]])
+    want_t = np.concatenate([g["seg_t"], g["edge_t"]])
+    want_p = np.concatenate([g["seg_p"], g["edge_p"]])
+    want_n = np.concatenate([g["seg_normal"], g["edge_normal"]])
+    idx, t, p, n = scenes[name].trace_rays(org, d, variant=r1.VARIANTS[variant])
+    assert np.array_equal(idx, want_idx), "hit sphere index differs for %d rays" % int((idx != want_idx).sum())
+    m = idx >= 0
+    assert m.sum() > 1000
+    assert np.abs(t[m] - want_t[m]).max() <= REL * np.abs(want_t[m]).max()
+    assert (np.abs(t[m] - want_t[m]) <= REL * np.abs(want_t[m])).all()
+    assert np.abs(p[m] - want_p[m]).max() <= REL * max(1.0, np.abs(want_p[m]).max())
+    assert np.abs(n[m] - want_n[m]).max() <= REL
+    # stronger than the contract: the exact path reproduces the reference's arithmetic bit for bit
+    assert np.array_equal(bits(t[m]), bits(want_t[m]))
+    assert np.array_equal(bits(n[m]), bits(want_n[m]))
+    assert (t[~m] == 0).all()
+
+
+@pytest.mark.parametrize("name", SCENES + ("synth4096",))
+def test_hit_matches_oracle_on_fresh_rays(r1, scenes, oracle, name):
+    """seeded random rays from points around the scene (inside spheres, on the ground, far away), incl. the 4096-sphere scene"""
+    rng = np.random.default_rng(1234)
+    n = 6000
+    org = (rng.normal(size=(n, 3)) * [8, 2, 8] + [0, 2, 0]).astype(np.float32)
+    org[: n // 4] = (rng.normal(size=(n // 4, 3)) * [12, 0.02, 7] + [0, 0.5, 0]).astype(np.float32)  # among the small spheres
+    d = rng.normal(size=(n, 3))
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    so = oracle.scene_create(name)
+    for t_min, t_max in ((0.001, float(np.finfo(np.float32).max)), (0.5, 6.0)):
+        want = oracle.hit(so, org, d, t_min, t_max)
+        got = scenes[name].trace_rays(org, d, t_min, t_max)
+        assert np.array_equal(got[0], want[0])
+        m = want[0] >= 0
+        assert m.sum() > 500
+        assert np.array_equal(bits(got[1][m]), bits(want[1][m]))
+        assert np.array_equal(bits(got[2][m]), bits(want[2][m]))
+        assert np.array_equal(bits(got[3][m]), bits(want[3][m]))
+    oracle.scene_destroy(so)
+
+
+def test_hit_empty_and_single(r1, scenes):
+    idx, t, p, n = scenes["small"].trace_rays(np.zeros((0, 3)), np.zeros((0, 3)))
+    assert idx.shape == (0,)
+    idx, t, p, n = scenes["small"].trace_rays([[0, 0, 5]], [[0, 0, -1]])
+    assert idx[0] == 0 and t[0] == pytest.approx(5.5)
+
+
+# ---- scatter() / camera -------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", SCENES)
+def test_scatter_matches_reference_golden(r1, scenes, golden_rays, name):
+    g = golden_rays[name]
+    m = (g["seg_index"] >= 0) & (g["seg_depth"] < 50)
+    ok, att, dout = scenes[name].scatter(g["seg_dir"][m], g["seg_p"][m], g["seg_normal"][m], g["seg_index"][m],
+                                         g["seg_rand_sphere"][m], g["seg_rand_u"][m])
+    assert np.array_equal(ok, g["seg_scat_ok"][m])
+    assert np.array_equal(bits(att), bits(g["seg_atten"][m])) or np.abs(att - g["seg_atten"][m]).max() < 1e-7
+    err = np.abs(dout - g["seg_scat_dir"][m]).max(axis=1)
+    assert err.max() <= REL, "scatter direction off by %g" % err.max()
+    kinds = scenes[name].soa()["kind"][g["seg_index"][m]]
+    for k in (0, 1, 2):
+        assert (kinds == k).sum() > 20, "material %d under-sampled" % k
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_scatter_matches_oracle_on_fresh_inputs(r1, scenes, oracle, name):
+    rng = np.random.default_rng(99)
+    n = 4000
+    soa = scenes[name].soa()
+    real = np.where(soa["inv_radius"] > 0)[0]
+    idx = rng.choice(real, n).astype(np.int32)
+    nrm = rng.normal(size=(n, 3)); nrm = (nrm / np.linalg.norm(nrm, axis=1, keepdims=True)).astype(np.float32)
+    din = rng.normal(size=(n, 3)); din = (din / np.linalg.norm(din, axis=1, keepdims=True)).astype(np.float32)
+    ctr = np.stack([soa["cx"][idx], soa["cy"][idx], soa["cz"][idx]], 1)
+    p = (ctr + nrm / soa["inv_radius"][idx][:, None]).astype(np.float32)
+    rs = rng.uniform(-1, 1, size=(n * 3, 3)); rs = rs[(rs ** 2).sum(1) < 1][:n].astype(np.float32)
+    ru = rng.uniform(0, 1, n).astype(np.float32)
+    so = oracle.scene_create(name)
+    want = oracle.scatter(so, din, p, nrm, idx, rs, ru)
+    got = scenes[name].scatter(din, p, nrm, idx, rs, ru)
+    oracle.scene_destroy(so)
+    # metal's return flag is dot(dir, n) > 0: ignore the sign within rounding of zero
+    dotn = (want[2] * nrm).sum(1)
+    firm = np.abs(dotn) > 1e-5
+    assert np.array_equal(got[0][firm], want[0][firm])
+    assert np.abs(got[1] - want[1]).max() < 1e-7
+    # lambertian directions are ill-conditioned when normal + rand_sphere is short: (p + n + rs) - p loses |p| ulps
+    cond = np.linalg.norm(nrm + rs, axis=1) > 0.05
+    assert np.abs(got[2] - want[2])[cond].max() <= REL
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_camera_rays_match_reference_golden(r1, scenes, golden_rays, name):
+    g = golden_rays[name]
+    m = g["seg_depth"] == 0
+    org, d = scenes[name].get_ray(g["seg_cam_su"][m], g["seg_cam_tv"][m], g["seg_cam_disk"][m])
+    assert np.abs(org - g["seg_org"][m]).max() <= REL * np.abs(g["seg_org"][m]).max()
+    assert np.abs(d - g["seg_dir"][m]).max() <= REL
+
+
+# ---- RNG ------------------------------------------------------------------------------------------------------------------------
+
+def test_rng_is_counter_based_and_uniform(r1):
+    a = r1.rng_draws(123, 45, 0, 64)
+    assert np.array_equal(a, r1.rng_draws(123, 45, 0, 64)), "same (pixel, sample, seed) -> same stream"
+    assert np.array_equal(a[:16], r1.rng_draws(123, 45, 0, 16)), "draw k does not depend on how many draws follow"
+    assert not np.array_equal(a, r1.rng_draws(124, 45, 0, 64))
+    assert not np.array_equal(a, r1.rng_draws(123, 46, 0, 64))
+    assert not np.array_equal(a, r1.rng_draws(123, 45, 1, 64))
+    # first draws of 20000 consecutive (pixel, sample) keys: uniform in [0,1) at 24-bit resolution, uncorrelated
+    firsts = np.array([r1.rng_draws(p, s, 0, 2) for p in range(200) for s in range(100)], np.uint32)
+    u = (firsts >> 8).astype(np.float64) / 2 ** 24
+    assert abs(u.mean() - 0.5) < 0.01 and abs(u.var() - 1 / 12) < 0.005
+    hist, _ = np.histogram(u[:, 0], bins=64, range=(0, 1))
+    chi2 = ((hist - hist.mean()) ** 2 / hist.mean()).sum()
+    assert chi2 < 120, chi2  # 63 dof, p ~ 1e-5
+    assert abs(np.corrcoef(u[:, 0], u[:, 1])[0, 1]) < 0.03
+    assert abs(np.corrcoef(u[:-1, 0], u[1:, 0])[0, 1]) < 0.03
+
+
+# ---- the trace loop: statistics against the reference ------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", SCENES)
+def test_image_rmse_and_rays_per_sample_vs_reference(r1, scenes, golden_render, ref_stats, name):
+    """matched high spp: reference 16384 spp (tests/golden) vs GPU 16384 spp at 320x180."""
+    g = golden_render[name]
+    h, w = g["rgb"].shape[:2]
+    spp = int(g["spp"])
+    rgb, res = scenes[name].render(w, h, spp)
+    e = rmse(rgb, g["rgb"])
+    assert e <= 1.0, "per-channel RMSE %.3f / 255 exceeds 1/255" % e
+    rps = res.num_rays / (w * h * spp)
+    ref = ref_stats["default_workload"][name]["rays_per_sample"]
+    assert abs(rps / ref - 1) < 0.005, (rps, ref)
+    assert res.num_samples == w * h * spp
+    # no systematic bias per channel either
+    bias = (rgb.astype(np.float64) - g["rgb"]).mean(axis=(0, 1))
+    assert np.abs(bias).max() < 0.25, bias
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_full_size_default_workload(r1, scenes, ref_stats, name):
+    """BASELINE.json configs 1-3 at full size: 1280x720x250, depth 50."""
+    rgb, res = scenes[name].render(1280, 720, 250)
+    ref = ref_stats["default_workload"][name]
+    assert abs(res.num_rays / np.mean(ref["num_rays"]) - 1) < 0.005
+    assert rgb.shape == (720, 1280, 3)
+    # sky at the top of the picture (last rows: row 0 is the BOTTOM), gradient blue > red
+    top = rgb[-20:].reshape(-1, 3).mean(0)
+    assert top[2] > top[0] and top[2] > 200
+    assert res.launches == 2 and res.kernel_ms > 0 and res.trace_ms <= res.kernel_ms
+
+
+def test_synth4096_against_oracle_render(r1, scenes, oracle):
+    """config 5: no reference image exists (MAX_SPHERES = 1024 in the reference, rayweek1.cpp:174) -> oracle render."""
+    w, h, spp = 96, 54, 64
+    so = oracle.scene_create("synth4096", w, h)
+    want, rays_o, _ = oracle.render(so, w, h, spp, threads=8)
+    oracle.scene_destroy(so)
+    rgb, res = scenes["synth4096"].render(w, h, spp * 8)
+    assert abs(res.num_rays / (w * h * spp * 8) / (rays_o / (w * h * spp)) - 1) < 0.02
+    assert rmse(rgb, want) < 9.0  # the oracle side has only 64 spp
+
+
+# ---- determinism / partition invariance --------------------------------------------------------------------------------
+
+def test_bitwise_invariance(r1, scenes):
+    """same (w, h, spp, seed) -> same bytes for: repeat runs, the scalar scan, 2 / 3 / 8 interleaved ranks, other CTA counts"""
+    s = scenes["large"]
+    w, h, spp = 200, 117, 40
+    base, r0 = s.render(w, h, spp)
+    again, r1_ = s.render(w, h, spp)
+    assert np.array_equal(base, again) and r0.num_rays == r1_.num_rays
+    scal, rs = s.render(w, h, spp, variant=r1.VARIANT_MEGAKERNEL_SCALAR)
+    assert np.array_equal(base, scal) and rs.num_rays == r0.num_rays
+    more, rm = s.render(w, h, spp, blocks_per_sm=2)
+    assert np.array_equal(base, more) and rm.num_rays == r0.num_rays
+    for world in (2, 3, 8):
+        parts, rays = [], 0
+        for rank in range(world):
+            rgb, res = s.render(w, h, spp, rank=rank, world=world)
+            parts.append(rgb)
+            rays += res.num_rays
+        assert np.array_equal(r1.assemble_rows(parts, h), base), world
+        assert rays == r0.num_rays
+    other, _ = s.render(w, h, spp, seed=1)
+    assert not np.array_equal(base, other)
+    assert rmse(base, other) < 12
+
+
+def test_edge_sizes_and_depth_cap(r1, scenes):
+    s = scenes["medium"]
+    rgb, res = s.render(1, 1, 1)
+    assert rgb.shape == (1, 1, 3) and 1 <= res.num_rays <= 51
+    rgb, res = s.render(33, 7, 3)                      # ragged: width not a warp multiple, height < row tile
+    assert res.num_samples == 33 * 7 * 3 and rgb.any()
+    rgb, res = s.render(16, 9, 5, max_bounces=0)       # cap 0: exactly one ray per sample, hits are black
+    assert res.num_rays == 16 * 9 * 5
+    rgb1, res1 = s.render(64, 36, 16, max_bounces=1)
+    rgb50, res50 = s.render(64, 36, 16, max_bounces=50)
+    assert res1.num_rays < res50.num_rays <= 64 * 36 * 16 * 51
+    rgb, res = s.render(40, 10, 2, rank=7, world=8)    # a rank that owns no rows
+    assert rgb.shape[0] == 0 and res.num_rays == 0
+    rgb, res = s.render(640, 360, 1)
+    assert res.num_samples == 640 * 360
+
+
+# ---- the reference's surface ------------------------------------------------------------------------------------------------
+
+def test_benchmark_surface(r1, tmp_path, monkeypatch, capfd):
+    monkeypatch.chdir(tmp_path)
+    r1.configure(width=160, height=90, spp=32, quiet=False)
+    try:
+        scene = r1.create_small_scene()
+        pixels = np.zeros((90, 160, 3), np.uint8)
+        res = r1.benchmark(scene, pixels, True, "small")
+        with pytest.raises(r1.Rays1Error):
+            scene.handle  # consumed (delete scene, rayweek1.cpp:905)
+        out = capfd.readouterr().out.splitlines()
+        assert out[0] == "small"
+        assert out[1].startswith("elapsed time:   ") and out[1].endswith("s")
+        assert out[2] == "total samples:  %d" % (160 * 90 * 32)
+        assert out[3] == "total rays:     %d" % res.num_rays
+        assert out[4].startswith("mrays/s:        ")
+        assert out[5].startswith("threads:        1/")
+        assert out[6].startswith("tile size:      ")
+        assert abs(res.num_rays / (160 * 90 * 32) / 1.798 - 1) < 0.02
+        raw = open(tmp_path / "out_small.tga", "rb").read()
+        assert len(raw) == 18 + 160 * 90 * 3 and raw[2] == 2 and raw[16] == 24
+        body = np.frombuffer(raw[18:], np.uint8).reshape(90, 160, 3)
+        assert np.array_equal(body, pixels), "pixels were swapped to BGR in place, like the reference"
+        fresh, _ = r1.create_small_scene().render(160, 90, 32)
+        assert np.array_equal(body[:, :, ::-1], fresh)
+    finally:
+        r1.configure(width=1280, height=720, spp=250, quiet=True)
+
+
+def test_drop_in_executable(r1, tmp_path):
+    out = subprocess.run([r1.EXE_PATH, "-n", "2", "-w", "--spp", "4"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.splitlines()
+    assert [l for l in lines if l in ("small", "medium", "large")] == ["small", "small", "medium", "medium", "large", "large"]
+    assert sum(l == "total samples:  %d" % (1280 * 720 * 4) for l in lines) == 6
+    for name in ("small", "medium", "large"):
+        txt = open(tmp_path / ("out_%s.txt" % name)).read()
+        tok = txt.split("|")
+        assert tok[0] == "b200" and tok[1].endswith("s") and int(tok[2]) > 1280 * 720 * 4 and tok[3].endswith(" mrays/s") and tok[4] == ""
+        assert os.path.getsize(tmp_path / ("out_%s.tga" % name)) == 18 + 1280 * 720 * 3

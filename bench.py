@@ -123,13 +123,14 @@ def cpu_reference(workload, budget_s, steps, warmup):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="large", choices=sorted(WORKLOADS))
     ap.add_argument("--variant", default="mega", choices=["mega", "wavefront", "scalar"])
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work per reference step / baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--threads", type=int, default=0, help="threads per persistent CTA (512/768/1024; 0 = library default)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -189,7 +190,7 @@ def main():
     scene = r1.create_scene(scene_name, commit=False)
     r1._check(r1.lib.r1_scene_commit(scene.handle, local_rank), "r1_scene_commit")
     n_real = r1.REAL_SPHERES[scene_name]
-    n_pad = (scene.count() + 31) // 32 * 32
+    n_pad = (scene.count() + 7) // 8 * 8
 
     my_rows = r1.local_rows(H, row_tile, rank, world)
     max_rows = r1d.max_local_rows(H, row_tile, world)
@@ -197,7 +198,7 @@ def main():
     d_rays = torch.zeros(1, dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
-    kw = dict(width=W, height=H, spp=SPP, max_bounces=MB, variant=variant, seed=0, rank=rank, world=world, row_tile=row_tile, device=local_rank)
+    kw = dict(width=W, height=H, spp=SPP, max_bounces=MB, variant=variant, seed=0, rank=rank, world=world, row_tile=row_tile, device=local_rank, threads=args.threads)
 
     def step():
         """one pass of the hot path; returns (#kernels of ours launched, final image tensor on rank 0)"""

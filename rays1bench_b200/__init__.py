@@ -39,7 +39,7 @@ class Result(C.Structure):
 class RenderParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("spp", C.c_int32), ("max_bounces", C.c_int32),
                 ("variant", C.c_int32), ("seed", C.c_uint32), ("rank", C.c_int32), ("world", C.c_int32),
-                ("row_tile", C.c_int32), ("blocks_per_sm", C.c_int32), ("device", C.c_int32)]
+                ("row_tile", C.c_int32), ("blocks_per_sm", C.c_int32), ("threads", C.c_int32), ("device", C.c_int32)]
 
 
 def _load():
@@ -154,9 +154,9 @@ class Scene:
 
     # -- device entry points
     def render(self, width=SCREEN_W, height=SCREEN_H, spp=NUM_SAMPLES_PER_PIXEL, max_bounces=MAX_BOUNCES, variant=VARIANT_MEGAKERNEL,
-               seed=0, rank=0, world=1, row_tile=8, device=-1, blocks_per_sm=0):
+               seed=0, rank=0, world=1, row_tile=8, device=-1, blocks_per_sm=0, threads=0):
         """r1_render: host buffer out.  Returns (rgb[local_rows, width, 3] uint8 with row 0 = bottom, Result)."""
-        p = RenderParams(width, height, spp, max_bounces, variant, seed, rank, world, row_tile, blocks_per_sm, device)
+        p = RenderParams(width, height, spp, max_bounces, variant, seed, rank, world, row_tile, blocks_per_sm, threads, device)
         rows = int(lib.r1_local_rows(height, row_tile, rank, world))
         rgb = np.zeros((rows, width, 3), np.uint8)
         res = Result()
@@ -168,7 +168,7 @@ class Scene:
         """r1_render_device: asynchronous, device pointers (e.g. torch tensors' data_ptr())."""
         p = RenderParams(kw.get("width", SCREEN_W), kw.get("height", SCREEN_H), kw.get("spp", NUM_SAMPLES_PER_PIXEL),
                          kw.get("max_bounces", MAX_BOUNCES), kw.get("variant", VARIANT_MEGAKERNEL), kw.get("seed", 0), kw.get("rank", 0),
-                         kw.get("world", 1), kw.get("row_tile", 8), kw.get("blocks_per_sm", 0), kw.get("device", -1))
+                         kw.get("world", 1), kw.get("row_tile", 8), kw.get("blocks_per_sm", 0), kw.get("threads", 0), kw.get("device", -1))
         res = Result()
         _check(lib.r1_render_device(self.handle, C.byref(p), C.c_void_p(d_rgb_ptr), C.c_void_p(d_num_rays_ptr),
                                     C.c_void_p(stream_ptr or 0), C.byref(res)), "r1_render_device")

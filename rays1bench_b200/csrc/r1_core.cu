@@ -38,25 +38,32 @@ int fail(int code, const char *fmt, ...)
         if (e_ != cudaSuccess) return fail(R1_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-// Per-device state of a committed scene.  Scratch buffers grow on demand and are reused across renders.
+// Per-device state of a committed scene: one allocation [scan | exact | mat | inv_radius | kind], one H2D copy.
 struct DeviceCtx {
     int device = -1;
-    int sm_count = 0;
-    float4 *spheres = nullptr;  // [scan | exact], n_pad * 2 float4
-    float *inv_radius = nullptr;
-    float4 *mat = nullptr;
-    int32_t *kind = nullptr;
+    void *block = nullptr;
     r1::DevScene dev;
+};
+
+// Per-device scratch shared by every scene of the process (work-unit partial sums, counters, staging, events).
+// It outlives scenes so that a render does not pay cudaMalloc/cudaFree; renders on one device are serialised by the
+// caller, as the reference's benchmark() calls are (rayweek1.cpp:969-984).
+struct Scratch {
+    bool ready = false;
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
     float4 *partial = nullptr; size_t partial_cap = 0;
     unsigned int *unit_counter = nullptr;
     uint8_t *rgb = nullptr; size_t rgb_cap = 0;
     unsigned long long *num_rays = nullptr;
+    unsigned long long *host_rays = nullptr;  // pinned
     r1::WavefrontBuffers wf;
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
-    cudaStream_t last_stream = nullptr;
     uint32_t last_launches = 0, last_units = 0;
     uint64_t last_samples = 0;
 };
+
+std::mutex g_scratch_mutex;
+std::map<int, Scratch> g_scratch;
 
 }  // namespace
 
@@ -76,11 +83,27 @@ void free_ctx(DeviceCtx &c)
 {
     if (c.device < 0) return;
     cudaSetDevice(c.device);
-    cudaFree(c.spheres); cudaFree(c.inv_radius); cudaFree(c.mat); cudaFree(c.kind);
-    cudaFree(c.partial); cudaFree(c.unit_counter); cudaFree(c.rgb); cudaFree(c.num_rays);
-    r1::wavefront_free(c.wf);
-    for (auto &e : c.ev) if (e) cudaEventDestroy(e);
+    cudaFree(c.block);
     c = DeviceCtx();
+}
+
+int get_scratch(int device, Scratch **out)
+{
+    std::lock_guard<std::mutex> lock(g_scratch_mutex);
+    Scratch &sc = g_scratch[device];
+    if (!sc.ready) {
+        R1_CUDA(cudaSetDevice(device));
+        R1_CUDA(cudaDeviceGetAttribute(&sc.sm_count, cudaDevAttrMultiProcessorCount, device));
+        R1_CUDA(cudaDeviceGetAttribute(&sc.cc_major, cudaDevAttrComputeCapabilityMajor, device));
+        R1_CUDA(cudaDeviceGetAttribute(&sc.cc_minor, cudaDevAttrComputeCapabilityMinor, device));
+        R1_CUDA(cudaMalloc(&sc.unit_counter, sizeof(unsigned int)));
+        R1_CUDA(cudaMalloc(&sc.num_rays, sizeof(unsigned long long)));
+        R1_CUDA(cudaMallocHost(&sc.host_rays, sizeof(unsigned long long)));
+        for (auto &e : sc.ev) R1_CUDA(cudaEventCreate(&e));
+        sc.ready = true;
+    }
+    *out = &sc;
+    return R1_OK;
 }
 
 void v3_unit(float *v)
@@ -124,22 +147,35 @@ Partition partition(int width, int height, int row_tile, int rank, int world)
     return p;
 }
 
-template <bool kPacked, bool kStaged>
-int launch_megakernel(const DeviceCtx &c, const r1::RenderArgs &args, const r1_render_params &prm, cudaStream_t stream)
+// One persistent CTA per SM; kThreads = 512 / 768 / 1024 (4 / 6 / 8 warps per scheduler; ptxas fits 96 / 76 / 64 registers
+// without spills).  Shared memory = 16 + n_pad * 32 bytes.
+constexpr int kDefaultThreads = 1024;
+
+template <bool kPacked, bool kStaged, int kThreads>
+int launch_megakernel_t(int sm_count, const r1::RenderArgs &args, const r1_render_params &prm, cudaStream_t stream)
 {
-    // 512 threads x 1 CTA per SM: 16 warps/SM = 4 per scheduler; shared memory = 16 + n_pad * 32 bytes.
-    constexpr int kThreads = 512, kBlocks = 1;
+    constexpr int kBlocks = 1;
     auto kern = r1::megakernel<kPacked, kStaged, kThreads, kBlocks>;
     const size_t smem = kStaged ? 16 + (size_t)args.scene.n_pad * 32 : 0;
     R1_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = c.sm_count * kBlocks;
-    if (prm.blocks_per_sm > 0) grid = c.sm_count * prm.blocks_per_sm;
+    int grid = sm_count * kBlocks;
+    if (prm.blocks_per_sm > 0) grid = sm_count * prm.blocks_per_sm;
     // never launch more lanes than there are units
     const long long max_ctas = ((long long)args.n_units + kThreads - 1) / kThreads;
     if (grid > max_ctas) grid = (int)std::max<long long>(1, max_ctas);
     kern<<<grid, kThreads, smem, stream>>>(args);
     R1_CUDA(cudaGetLastError());
     return R1_OK;
+}
+
+template <bool kPacked, bool kStaged>
+int launch_megakernel(int sm_count, const r1::RenderArgs &args, const r1_render_params &prm, cudaStream_t stream)
+{
+    const int threads = prm.threads > 0 ? prm.threads : kDefaultThreads;
+    if (threads == 512) return launch_megakernel_t<kPacked, kStaged, 512>(sm_count, args, prm, stream);
+    if (threads == 768) return launch_megakernel_t<kPacked, kStaged, 768>(sm_count, args, prm, stream);
+    if (threads == 1024) return launch_megakernel_t<kPacked, kStaged, 1024>(sm_count, args, prm, stream);
+    return fail(R1_ERR_ARG, "threads must be 512, 768 or 1024 (got %d)", threads);
 }
 
 int validate(const r1_render_params *p)
@@ -269,20 +305,26 @@ int r1_scene_commit(r1_scene *scene, int device)
     R1_CUDA(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(R1_ERR_ARG, "device %d out of range (%d visible)", device, ndev);
     R1_CUDA(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    R1_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) return fail(R1_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    Scratch *scr = nullptr;
+    int rc = get_scratch(device, &scr);
+    if (rc) return rc;
+    if (scr->cc_major != 10) return fail(R1_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, scr->cc_major, scr->cc_minor);
 
     DeviceCtx &c = scene->ctx[device];
     if (c.device >= 0) free_ctx(c);
     c.device = device;
-    c.sm_count = prop.multiProcessorCount;
 
     const int n = (int)scene->cx.size();
-    const int n_pad = (n + 31) / 32 * 32;
+    const int n_pad = (n + 7) / 8 * 8;  // the reference's own padding (SIMD_WIDTH, rayweek1.cpp:38, 575)
     const float inf = std::numeric_limits<float>::infinity();
-    std::vector<float4> spheres(2 * (size_t)n_pad);
-    float *scan = reinterpret_cast<float *>(spheres.data());
+    // host image of the device block: [scan n_pad f4 | exact n_pad f4 | mat n_pad f4 | inv_radius n_pad f | kind n_pad i32]
+    const size_t bytes = (size_t)n_pad * (16 + 16 + 16 + 4 + 4);
+    std::vector<unsigned char> host(bytes, 0);
+    float *scan = reinterpret_cast<float *>(host.data());
+    float4 *exact = reinterpret_cast<float4 *>(host.data()) + n_pad;
+    float4 *mat = exact + n_pad;
+    float *inv_r = reinterpret_cast<float *>(mat + n_pad);
+    int32_t *kind = reinterpret_cast<int32_t *>(inv_r + n_pad);
     for (int i = 0; i < n_pad; ++i) {
         const bool real = i < n && scene->inv_radius[i] != 0;  // rayweek1.cpp:288-292: inv_radius == 0 spheres never hit
         const int g = i / 4, k = i % 4;
@@ -290,33 +332,22 @@ int r1_scene_commit(r1_scene *scene, int device)
         scan[16 * g + 4 + k] = real ? -scene->cy[i] : 0.0f;
         scan[16 * g + 8 + k] = real ? -scene->cz[i] : 0.0f;
         scan[16 * g + 12 + k] = real ? -(scene->radius_sq[i] * (1.0f + 1.0f / 256.0f)) : inf;
-        spheres[n_pad + i] = i < n ? make_float4(scene->cx[i], scene->cy[i], scene->cz[i], scene->radius_sq[i]) : make_float4(0, 0, 0, 0);
+        kind[i] = R1_MAT_NONE;
+        if (i < n) {
+            exact[i] = make_float4(scene->cx[i], scene->cy[i], scene->cz[i], scene->radius_sq[i]);
+            mat[i] = make_float4(scene->albedo[3 * i], scene->albedo[3 * i + 1], scene->albedo[3 * i + 2], scene->param[i]);
+            inv_r[i] = scene->inv_radius[i];
+            kind[i] = scene->kind[i];
+        }
     }
-    std::vector<float> inv_r(n_pad, 0.0f);
-    std::vector<float4> mat(n_pad, make_float4(0, 0, 0, 0));
-    std::vector<int32_t> kind(n_pad, R1_MAT_NONE);
-    for (int i = 0; i < n; ++i) {
-        inv_r[i] = scene->inv_radius[i];
-        mat[i] = make_float4(scene->albedo[3 * i], scene->albedo[3 * i + 1], scene->albedo[3 * i + 2], scene->param[i]);
-        kind[i] = scene->kind[i];
-    }
-    R1_CUDA(cudaMalloc(&c.spheres, spheres.size() * sizeof(float4)));
-    R1_CUDA(cudaMalloc(&c.inv_radius, n_pad * sizeof(float)));
-    R1_CUDA(cudaMalloc(&c.mat, n_pad * sizeof(float4)));
-    R1_CUDA(cudaMalloc(&c.kind, n_pad * sizeof(int32_t)));
-    R1_CUDA(cudaMalloc(&c.unit_counter, sizeof(unsigned int)));
-    R1_CUDA(cudaMalloc(&c.num_rays, sizeof(unsigned long long)));
-    R1_CUDA(cudaMemcpy(c.spheres, spheres.data(), spheres.size() * sizeof(float4), cudaMemcpyHostToDevice));
-    R1_CUDA(cudaMemcpy(c.inv_radius, inv_r.data(), n_pad * sizeof(float), cudaMemcpyHostToDevice));
-    R1_CUDA(cudaMemcpy(c.mat, mat.data(), n_pad * sizeof(float4), cudaMemcpyHostToDevice));
-    R1_CUDA(cudaMemcpy(c.kind, kind.data(), n_pad * sizeof(int32_t), cudaMemcpyHostToDevice));
-    for (auto &e : c.ev) R1_CUDA(cudaEventCreate(&e));
-
-    c.dev.scan = c.spheres;
-    c.dev.exact = c.spheres + n_pad;
-    c.dev.inv_radius = c.inv_radius;
-    c.dev.mat = c.mat;
-    c.dev.kind = c.kind;
+    R1_CUDA(cudaMalloc(&c.block, bytes));
+    R1_CUDA(cudaMemcpy(c.block, host.data(), bytes, cudaMemcpyHostToDevice));
+    float4 *d4 = reinterpret_cast<float4 *>(c.block);
+    c.dev.scan = d4;
+    c.dev.exact = d4 + n_pad;
+    c.dev.mat = d4 + 2 * (size_t)n_pad;
+    c.dev.inv_radius = reinterpret_cast<float *>(d4 + 3 * (size_t)n_pad);
+    c.dev.kind = reinterpret_cast<const int32_t *>(c.dev.inv_radius + n_pad);
     c.dev.n_pad = n_pad;
     c.dev.n_real = n;
     c.dev.cam = scene->cam;
@@ -362,6 +393,10 @@ int r1_render_device(r1_scene *scene, const r1_render_params *params, void *d_rg
     rc = get_ctx(scene, &cp, params->device);
     if (rc) return rc;
     DeviceCtx &c = *cp;
+    Scratch *xp = nullptr;
+    rc = get_scratch(c.device, &xp);
+    if (rc) return rc;
+    Scratch &x = *xp;
     if (!d_rgb || !d_num_rays) return fail(R1_ERR_ARG, "null device buffer");
     r1_render_params prm = *params;
     if (prm.row_tile <= 0) prm.row_tile = 8;
@@ -382,52 +417,53 @@ int r1_render_device(r1_scene *scene, const r1_render_params *params, void *d_rg
     a.seed = prm.seed;
     a.inv_w = 1.0f / prm.width; a.inv_h = 1.0f / prm.height;  // rayweek1.cpp:746
     a.inv_spp = (float)(1.0f / prm.spp);                       // rayweek1.cpp:765
+    a.magic_npix = r1::div_magic(a.npix_local);
+    a.magic_width = r1::div_magic((uint32_t)prm.width);
     a.rgb = (uint8_t *)d_rgb;
     a.num_rays = (unsigned long long *)d_num_rays;
-    a.unit_counter = c.unit_counter;
+    a.unit_counter = x.unit_counter;
 
-    c.last_stream = stream;
-    c.last_launches = 0;
-    c.last_units = a.n_units;
-    c.last_samples = (uint64_t)a.npix_local * (uint64_t)prm.spp;
+    x.last_launches = 0;
+    x.last_units = a.n_units;
+    x.last_samples = (uint64_t)a.npix_local * (uint64_t)prm.spp;
     R1_CUDA(cudaMemsetAsync(d_num_rays, 0, sizeof(unsigned long long), stream));
-    R1_CUDA(cudaEventRecord(c.ev[0], stream));
+    R1_CUDA(cudaEventRecord(x.ev[0], stream));
     if (a.npix_local > 0) {
-        rc = grow(c.partial, c.partial_cap, (size_t)a.n_units);
+        rc = grow(x.partial, x.partial_cap, (size_t)a.n_units);
         if (rc) return rc;
-        a.partial = c.partial;
-        R1_CUDA(cudaMemsetAsync(c.unit_counter, 0, sizeof(unsigned int), stream));
+        a.partial = x.partial;
+        R1_CUDA(cudaMemsetAsync(x.unit_counter, 0, sizeof(unsigned int), stream));
         const bool staged = c.dev.n_pad <= r1::kMaxStagedSpheres;
-        R1_CUDA(cudaEventRecord(c.ev[1], stream));
+        R1_CUDA(cudaEventRecord(x.ev[1], stream));
         if (prm.variant == R1_VARIANT_WAVEFRONT) {
             uint32_t launches = 0;
-            rc = r1::wavefront_render(c.wf, a, c.sm_count, stream, &launches);
+            rc = r1::wavefront_render(x.wf, a, x.sm_count, stream, &launches);
             if (rc) return fail(R1_ERR_CUDA, "wavefront: %s", cudaGetErrorString((cudaError_t)rc));
-            c.last_launches += launches;
+            x.last_launches += launches;
         } else {
             const bool packed = prm.variant == R1_VARIANT_MEGAKERNEL;
-            if (packed && staged) rc = launch_megakernel<true, true>(c, a, prm, stream);
-            else if (packed) rc = launch_megakernel<true, false>(c, a, prm, stream);
-            else if (staged) rc = launch_megakernel<false, true>(c, a, prm, stream);
-            else rc = launch_megakernel<false, false>(c, a, prm, stream);
+            if (packed && staged) rc = launch_megakernel<true, true>(x.sm_count, a, prm, stream);
+            else if (packed) rc = launch_megakernel<true, false>(x.sm_count, a, prm, stream);
+            else if (staged) rc = launch_megakernel<false, true>(x.sm_count, a, prm, stream);
+            else rc = launch_megakernel<false, false>(x.sm_count, a, prm, stream);
             if (rc) return rc;
-            c.last_launches += 1;
+            x.last_launches += 1;
         }
-        R1_CUDA(cudaEventRecord(c.ev[2], stream));
-        const int rgrid = (int)std::min<uint64_t>(((uint64_t)a.npix_local + 255) / 256, (uint64_t)c.sm_count * 8);
+        R1_CUDA(cudaEventRecord(x.ev[2], stream));
+        const int rgrid = (int)std::min<uint64_t>(((uint64_t)a.npix_local + 255) / 256, (uint64_t)x.sm_count * 8);
         r1::resolve<<<rgrid, 256, 0, stream>>>(a);
         R1_CUDA(cudaGetLastError());
-        c.last_launches += 1;
+        x.last_launches += 1;
     } else {
-        R1_CUDA(cudaEventRecord(c.ev[1], stream));
-        R1_CUDA(cudaEventRecord(c.ev[2], stream));
+        R1_CUDA(cudaEventRecord(x.ev[1], stream));
+        R1_CUDA(cudaEventRecord(x.ev[2], stream));
     }
-    R1_CUDA(cudaEventRecord(c.ev[3], stream));
+    R1_CUDA(cudaEventRecord(x.ev[3], stream));
     if (result) {
         memset(result, 0, sizeof(*result));
-        result->num_samples = c.last_samples;
-        result->launches = c.last_launches;
-        result->n_units = c.last_units;
+        result->num_samples = x.last_samples;
+        result->launches = x.last_launches;
+        result->n_units = x.last_units;
     }
     return R1_OK;
 }
@@ -437,17 +473,20 @@ int r1_render_wait(r1_scene *scene, int device, r1_result *result)
     DeviceCtx *cp = nullptr;
     int rc = get_ctx(scene, &cp, device);
     if (rc) return rc;
-    DeviceCtx &c = *cp;
-    R1_CUDA(cudaEventSynchronize(c.ev[3]));
+    Scratch *xp = nullptr;
+    rc = get_scratch(cp->device, &xp);
+    if (rc) return rc;
+    Scratch &x = *xp;
+    R1_CUDA(cudaEventSynchronize(x.ev[3]));
     if (result) {
         float ms_all = 0, ms_trace = 0;
-        R1_CUDA(cudaEventElapsedTime(&ms_all, c.ev[0], c.ev[3]));
-        R1_CUDA(cudaEventElapsedTime(&ms_trace, c.ev[1], c.ev[2]));
+        R1_CUDA(cudaEventElapsedTime(&ms_all, x.ev[0], x.ev[3]));
+        R1_CUDA(cudaEventElapsedTime(&ms_trace, x.ev[1], x.ev[2]));
         result->kernel_ms = ms_all;
         result->trace_ms = ms_trace;
-        result->num_samples = c.last_samples;
-        result->launches = c.last_launches;
-        result->n_units = c.last_units;
+        result->num_samples = x.last_samples;
+        result->launches = x.last_launches;
+        result->n_units = x.last_units;
     }
     return R1_OK;
 }
@@ -461,21 +500,23 @@ int r1_render(r1_scene *scene, const r1_render_params *params, uint8_t *rgb_host
     DeviceCtx *cp = nullptr;
     rc = get_ctx(scene, &cp, params->device);
     if (rc) return rc;
-    DeviceCtx &c = *cp;
+    Scratch *xp = nullptr;
+    rc = get_scratch(cp->device, &xp);
+    if (rc) return rc;
+    Scratch &x = *xp;
     const Partition part = partition(params->width, params->height, params->row_tile, params->rank, params->world);
     const size_t bytes = (size_t)part.npix_local * 3;
-    rc = grow(c.rgb, c.rgb_cap, std::max<size_t>(bytes, 16));
+    rc = grow(x.rgb, x.rgb_cap, std::max<size_t>(bytes, 16));
     if (rc) return rc;
     r1_result res;
-    rc = r1_render_device(scene, params, c.rgb, c.num_rays, nullptr, &res);
+    rc = r1_render_device(scene, params, x.rgb, x.num_rays, nullptr, &res);
     if (rc) return rc;
-    unsigned long long rays = 0;
-    if (bytes) R1_CUDA(cudaMemcpyAsync(rgb_host, c.rgb, bytes, cudaMemcpyDeviceToHost, nullptr));
-    R1_CUDA(cudaMemcpyAsync(&rays, c.num_rays, sizeof(rays), cudaMemcpyDeviceToHost, nullptr));
+    if (bytes) R1_CUDA(cudaMemcpyAsync(rgb_host, x.rgb, bytes, cudaMemcpyDeviceToHost, nullptr));
+    R1_CUDA(cudaMemcpyAsync(x.host_rays, x.num_rays, sizeof(unsigned long long), cudaMemcpyDeviceToHost, nullptr));
     R1_CUDA(cudaStreamSynchronize(nullptr));
     rc = r1_render_wait(scene, params->device, &res);
     if (rc) return rc;
-    res.num_rays = rays;
+    res.num_rays = *x.host_rays;
     res.elapsed_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (result) *result = res;
     return R1_OK;
@@ -587,7 +628,7 @@ int r1_fma_peak(int device, int packed, double *tflops, double *sm_mhz_est)
     const int iters = 1 << 16, threads = 256, grid = prop.multiProcessorCount * 8;
     cudaEvent_t e0, e1;
     R1_CUDA(cudaEventCreate(&e0)); R1_CUDA(cudaEventCreate(&e1));
-    double best_ms = 1e30;
+    double best_ms = 1e30, mhz = 0;
     for (int rep = 0; rep < 4; ++rep) {  // first repetition is the warm-up
         R1_CUDA(cudaEventRecord(e0));
         if (packed) r1::fma_peak_kernel<true><<<grid, threads>>>(iters, 0.5f, sink.as<float>(), cyc.as<long long>());
@@ -596,15 +637,15 @@ int r1_fma_peak(int device, int packed, double *tflops, double *sm_mhz_est)
         R1_CUDA(cudaEventSynchronize(e1));
         float ms = 0;
         R1_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-        if (rep > 0 && ms < best_ms) best_ms = ms;
+        long long cycles = 0;
+        R1_TRY(cyc.download(&cycles, sizeof(cycles)));
+        // all 8 x 256-thread CTAs per SM are resident (one wave), so one CTA's cycle count spans the kernel
+        if (rep > 0 && ms < best_ms) { best_ms = ms; mhz = (double)cycles / (ms * 1e-3) / 1e6; }
     }
-    long long cycles = 0;
-    R1_TRY(cyc.download(&cycles, sizeof(cycles)));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     const double fmas = (double)grid * threads * (double)iters * 16.0;  // 16 scalar FMAs or 8 packed (= 16) per iteration
     *tflops = 2.0 * fmas / (best_ms * 1e-3) / 1e12;
-    // one CTA's cycle count spans ~1/waves of the kernel: grid = 8 CTAs/SM of 256 threads all resident -> one wave
-    if (sm_mhz_est) *sm_mhz_est = (double)cycles / (best_ms * 1e-3) / 1e6;
+    if (sm_mhz_est) *sm_mhz_est = mhz;
     return R1_OK;
 }
 

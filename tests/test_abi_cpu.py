@@ -92,7 +92,7 @@ def test_scene_abi_argument_checking(r1):
     assert lib.r1_scene_get_soa(sc, cx, cy, cz, r2, ir, kind, al, pa) == 0
     assert pa[0] == 1.0, "Metal fuzz is clamped to <= 1 (rayweek1.cpp:424)"
     assert lib.r1_scene_commit(sc, 0) == -2 and b"camera" in lib.r1_last_error()  # camera not set
-    p = r1.RenderParams(16, 9, 1, 50, 0, 0, 0, 1, 8, 0, -1)
+    p = r1.RenderParams(16, 9, 1, 50, 0, 0, 0, 1, 8, 0, 0, -1)
     res = r1.Result()
     assert lib.r1_render(sc, C.byref(p), np.zeros(16 * 9 * 3, np.uint8), C.byref(res)) == -2  # not committed
     p.world = 0

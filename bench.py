@@ -158,6 +158,7 @@ def main():
         return
 
     # -------------------------------------------------------------------------------------------- B200 arm
+    os.environ["NCCL_DEBUG"] = os.environ.get("R1_NCCL_DEBUG", "WARN")  # NCCL's version banner goes to stdout otherwise
     import torch
     import torch.distributed as dist
 
@@ -230,7 +231,9 @@ def main():
         barrier()
         if timed:
             total_ms += e0.elapsed_time(e1)
-            trace_ms += scene.render_wait(local_rank).trace_ms
+            waited = scene.render_wait(local_rank)
+            trace_ms += waited.trace_ms
+            n_l += waited.launches - (n_l if world == 1 else n_l - 1)  # wavefront: the loop's kernels are counted on the device
             total_rays += int(d_rays.item()) if rank == 0 else 0  # for N > 1 the reduced total lives on rank 0
             launches += n_l
     clocks = sampler.end() if sampler else None
@@ -285,7 +288,7 @@ def main():
     achieved = total_rays * f_ray / (ms_trace * 1e-3) / 1e12 / world  # per GPU
     n_chunks = (SPP + max(8, (SPP + 15) // 16) - 1) // max(8, (SPP + 15) // 16)
     hbm_bytes = W * H * (n_chunks * 16 * 2 + 3) + n_pad * 32 * sm_count
-    roofline = {"bound": "fp32_fma", "kernel": "r1::megakernel" if args.variant != "wavefront" else "r1::wf_intersect", "achieved": achieved,
+    roofline = {"bound": "fp32_fma", "kernel": "r1::megakernel" if args.variant != "wavefront" else "r1::wf_intersect + wf_shade (graph loop)", "achieved": achieved,
                 "peak": peak_meas, "unit": "TFLOP/s", "frac": achieved / peak_meas,
                 "peak_source": "FFMA/FFMA2 chain microbenchmark on this GPU (r1_fma_peak), per GPU; scalar %.1f / packed %.1f TFLOP/s at ~%.0f MHz" %
                                (peak_scalar, peak_packed, mhz_est),

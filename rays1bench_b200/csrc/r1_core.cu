@@ -60,6 +60,7 @@ struct Scratch {
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
     uint32_t last_launches = 0, last_units = 0;
     uint64_t last_samples = 0;
+    bool last_wavefront = false;
 };
 
 std::mutex g_scratch_mutex;
@@ -424,6 +425,7 @@ int r1_render_device(r1_scene *scene, const r1_render_params *params, void *d_rg
     a.unit_counter = x.unit_counter;
 
     x.last_launches = 0;
+    x.last_wavefront = prm.variant == R1_VARIANT_WAVEFRONT;
     x.last_units = a.n_units;
     x.last_samples = (uint64_t)a.npix_local * (uint64_t)prm.spp;
     R1_CUDA(cudaMemsetAsync(d_num_rays, 0, sizeof(unsigned long long), stream));
@@ -487,6 +489,11 @@ int r1_render_wait(r1_scene *scene, int device, r1_result *result)
         result->num_samples = x.last_samples;
         result->launches = x.last_launches;
         result->n_units = x.last_units;
+        if (x.last_wavefront && x.wf.d_iterations) {  // wavefront: 3 kernels per loop iteration, counted on the device
+            uint32_t iters = 0;
+            R1_CUDA(cudaMemcpy(&iters, x.wf.d_iterations, sizeof(iters), cudaMemcpyDeviceToHost));
+            result->launches += 3 * iters;
+        }
     }
     return R1_OK;
 }

@@ -64,6 +64,56 @@ __device__ __host__ __forceinline__ int global_row(int lr, int row_tile, int ran
     return ((lr / row_tile) * world + rank) * row_tile + (lr % row_tile);
 }
 
+// ------------------------------------------------------------------------------------------------ shared path steps
+// The three steps of the per-path state machine, shared by the megakernel and the wavefront kernels so that both
+// execute the same instructions on the same values (bit-identical images).
+
+// unit -> (pixel, first sample, end sample)
+__device__ __forceinline__ void unit_begin(const RenderArgs &a, uint32_t unit, uint32_t &pixel, float &fx, float &fy, int &s, int &s_end)
+{
+    const uint32_t c = fast_div(unit, a.magic_npix), lp = unit - c * a.npix_local;
+    const int lr = (int)fast_div(lp, a.magic_width), x = (int)(lp - (uint32_t)lr * (uint32_t)a.width);
+    const int y = global_row(lr, a.row_tile, a.rank, a.world);
+    pixel = (uint32_t)y * (uint32_t)a.width + (uint32_t)x;
+    fx = (float)x; fy = (float)y;
+    s = (int)c * a.samples_per_unit;
+    s_end = min(s + a.samples_per_unit, a.spp);
+}
+
+// start sample s of a pixel: jitter (rayweek1.cpp:759), lens disk + camera ray (:760, :381-386)
+__device__ __forceinline__ void primary_ray(const RenderArgs &a, uint32_t pixel, float fx, float fy, int s, Rng &rng, f3 &o, f3 &d)
+{
+    rng.seed(pixel, (uint32_t)s, a.seed);
+    const float u = fmul(fadd(rng.rand01(), fx), a.inv_w), v = fmul(fadd(rng.rand01(), fy), a.inv_h);
+    float px, py;
+    random_in_unit_disk(rng, px, py);
+    camera_ray(a.scene.cam, u, v, px, py, o, d);
+}
+
+// color() body after hit() (rayweek1.cpp:515-536).  Returns true when the path ends (contrib = its radiance);
+// otherwise o / d / thr / depth hold the scattered ray.  `e` is the hit sphere's exact record.
+__device__ __forceinline__ bool shade_step(const RenderArgs &a, int hit, float t, float4 e, f3 &o, f3 &d, f3 &thr, int &depth, Rng &rng, f3 &contrib)
+{
+    contrib = mk3(0, 0, 0);
+    if (hit < 0) {
+        const f3 sk = sky(d);
+        contrib = mk3(fmul(thr.x, sk.x), fmul(thr.y, sk.y), fmul(thr.z, sk.z));
+        return true;
+    }
+    if (depth >= a.max_bounces) return true;   // :523 -- no scatter (and no RNG draw) past the cap
+    f3 p, n, atten, nd, rs = mk3(0, 0, 0);
+    float ru = 0.0f;
+    hit_finalise(e, __ldg(a.scene.inv_radius + hit), o, d, t, p, n);
+    const int kind = __ldg(a.scene.kind + hit);
+    const float4 mat = __ldg(a.scene.mat + hit);
+    if (kind == 2) ru = rng.rand01();
+    else rs = random_in_unit_sphere(rng);
+    if (!scatter(kind, mat, d, p, n, rs, ru, atten, nd)) return true;
+    thr = mk3(fmul(thr.x, atten.x), fmul(thr.y, atten.y), fmul(thr.z, atten.z));
+    o = p; d = nd; ++depth;
+    return false;
+}
+
 // ------------------------------------------------------------------------------------------------ megakernel
 // Persistent CTAs; every lane runs  loop { take a unit | start a sample | SCAN | shade }  so that all 32 lanes enter
 // every scan with a live ray and divergence is confined to the short fetch / generate / shade steps.
@@ -106,13 +156,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel(const __gri
             if (want) {
                 unit = base + __popc(need & ((1u << lane) - 1u));
                 if (unit < a.n_units) {
-                    const uint32_t c = fast_div(unit, a.magic_npix), lp = unit - c * a.npix_local;
-                    const int lr = (int)fast_div(lp, a.magic_width), x = (int)(lp - (uint32_t)lr * (uint32_t)a.width);
-                    const int y = global_row(lr, a.row_tile, a.rank, a.world);
-                    pixel = (uint32_t)y * (uint32_t)a.width + (uint32_t)x;
-                    fx = (float)x; fy = (float)y;
-                    s = (int)c * a.samples_per_unit;
-                    s_end = min(s + a.samples_per_unit, a.spp);
+                    unit_begin(a, unit, pixel, fx, fy, s, s_end);
                     acc = mk3(0, 0, 0);
                     active = true; need_primary = true;
                 } else {
@@ -123,13 +167,9 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel(const __gri
         }
         if (__all_sync(kFull, exhausted)) break;
 
-        // -- start a sample: jitter (rayweek1.cpp:759), lens disk + camera ray (:760, :381-386)
+        // -- start a sample
         if (active && need_primary) {
-            rng.seed(pixel, (uint32_t)s, a.seed);
-            const float u = fmul(fadd(rng.rand01(), fx), a.inv_w), v = fmul(fadd(rng.rand01(), fy), a.inv_h);
-            float px, py;
-            random_in_unit_disk(rng, px, py);
-            camera_ray(a.scene.cam, u, v, px, py, o, d);
+            primary_ray(a, pixel, fx, fy, s, rng, o, d);
             thr = mk3(1, 1, 1);
             depth = 0;
             need_primary = false;
@@ -143,26 +183,9 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel(const __gri
         // -- color() body (rayweek1.cpp:515-536)
         if (active) {
             ++nrays;
-            bool done = true;
-            f3 contrib = mk3(0, 0, 0);
-            if (hit < 0) {
-                const f3 sk = sky(d);
-                contrib = mk3(fmul(thr.x, sk.x), fmul(thr.y, sk.y), fmul(thr.z, sk.z));
-            } else if (depth < a.max_bounces) {
-                f3 p, n, atten, nd, rs = mk3(0, 0, 0);
-                float ru = 0.0f;
-                hit_finalise(s_exact[hit], __ldg(a.scene.inv_radius + hit), o, d, t, p, n);
-                const int kind = __ldg(a.scene.kind + hit);
-                const float4 mat = __ldg(a.scene.mat + hit);
-                if (kind == 2) ru = rng.rand01();
-                else rs = random_in_unit_sphere(rng);
-                if (scatter(kind, mat, d, p, n, rs, ru, atten, nd)) {
-                    thr = mk3(fmul(thr.x, atten.x), fmul(thr.y, atten.y), fmul(thr.z, atten.z));
-                    o = p; d = nd; ++depth;
-                    done = false;
-                }
-            }
-            if (done) {
+            f3 contrib;
+            const float4 e = hit >= 0 ? s_exact[hit] : make_float4(0, 0, 0, 0);
+            if (shade_step(a, hit, t, e, o, d, thr, depth, rng, contrib)) {
                 acc = add3(acc, contrib);
                 if (++s == s_end) {
                     a.partial[unit] = make_float4(acc.x, acc.y, acc.z, 0.0f);

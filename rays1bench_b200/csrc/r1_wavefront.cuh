@@ -1,26 +1,310 @@
-// r1_wavefront.cuh -- wavefront variant (generate / intersect / shade kernels over compacted ray queues).
+// r1_wavefront.cuh -- wavefront variant of the trace loop: the same per-path state machine as the megakernel
+// (unit_begin / primary_ray / shade_step), but with the path state in HBM and the stages split into kernels:
+//
+//   wf_init       every slot takes a unit and generates its first primary ray
+//   loop (a CUDA-graph WHILE node: the host never waits inside the loop)
+//     wf_intersect  all live slots: Hitable::hit with R rays per lane sharing each sphere load; classifies each slot
+//                   (miss / lambertian / metal / dielectric) and appends it to that class's queue, compacted with
+//                   warp ballot + one atomic per warp per class
+//     wf_shade      walks the queues class by class, so a warp shades 32 rays of ONE material (or 32 misses, which also
+//                   start the next sample / take the next unit): full lanes where the megakernel runs 5-12 of 32
+//     wf_decide     one thread: loop again while any slot is alive; resets the queue counters
+//
+// Every slot sums its unit's samples in order exactly like a megakernel lane, so both variants write bit-identical
+// partial sums.  State: 88 bytes per slot (SoA), ~2.4 M slots.
 #pragma once
 #include "r1_kernels.cuh"
 
 namespace r1 {
 
+constexpr int kWfRays = 4;          // rays per lane in wf_intersect
+constexpr int kWfThreads = 512;     // 128 registers per thread, one CTA per SM
+constexpr uint32_t kDead = 0xffffffffu;
+
+struct WfState {
+    float4 *ray_o;      // origin.xyz, -
+    float4 *ray_d;      // dir.xyz, -
+    float4 *thr;        // throughput.rgb, depth (int bits)
+    float4 *acc;        // unit accumulator.rgb, -
+    uint4 *meta;        // unit (kDead = slot retired), sample index, rng key, rng ctr
+    float *hit_t;
+    int32_t *hit_idx;
+    uint32_t *queue;    // 4 classes x n_slots slot indices
+    uint32_t *counters; // [0..3] class queue lengths, [4] live slots after shade, [5] loop iterations so far
+    uint32_t n_slots;
+};
+
 struct WavefrontBuffers {
     void *pool = nullptr;
     size_t pool_bytes = 0;
+    cudaGraphExec_t exec = nullptr;
+    uint32_t *d_iterations = nullptr;  // device counter of loop iterations of the last render
 };
 
 inline void wavefront_free(WavefrontBuffers &b)
 {
+    if (b.exec) cudaGraphExecDestroy(b.exec);
     if (b.pool) cudaFree(b.pool);
-    b.pool = nullptr;
-    b.pool_bytes = 0;
+    b = WavefrontBuffers();
 }
 
-// returns a cudaError_t (0 = ok)
-inline int wavefront_render(WavefrontBuffers &, const RenderArgs &, int, cudaStream_t, uint32_t *launches)
+__device__ __forceinline__ void wf_store_path(const WfState &w, uint32_t slot, f3 o, f3 d, f3 thr, int depth, uint32_t unit, int s, const Rng &rng)
+{
+    w.ray_o[slot] = make_float4(o.x, o.y, o.z, 0.0f);
+    w.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.0f);
+    w.thr[slot] = make_float4(thr.x, thr.y, thr.z, __int_as_float(depth));
+    w.meta[slot] = make_uint4(unit, (uint32_t)s, rng.key, rng.ctr);
+}
+
+// slot i starts unit i (the unit counter is preset to min(n_slots, n_units))
+__global__ void __launch_bounds__(256) wf_init(const __grid_constant__ RenderArgs a, const __grid_constant__ WfState w)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.unit_counter = a.n_units < w.n_slots ? a.n_units : w.n_slots;
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < w.n_slots; slot += gridDim.x * blockDim.x) {
+        if (slot < a.n_units) {
+            uint32_t pixel; float fx, fy; int s, s_end;
+            unit_begin(a, slot, pixel, fx, fy, s, s_end);
+            Rng rng; f3 o, d;
+            primary_ray(a, pixel, fx, fy, s, rng, o, d);
+            wf_store_path(w, slot, o, d, mk3(1, 1, 1), 0, slot, s, rng);
+            w.acc[slot] = make_float4(0, 0, 0, 0);
+        } else {
+            w.meta[slot] = make_uint4(kDead, 0, 0, 0);
+        }
+    }
+}
+
+// Hitable::hit for every live slot; R rays per lane; classification + queue compaction.
+template <int R>
+__global__ void __launch_bounds__(kWfThreads, 1) wf_intersect(const __grid_constant__ RenderArgs a, const __grid_constant__ WfState w)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4 *s_spheres = reinterpret_cast<float4 *>(smem_raw + 16);
+    stage_spheres(a.scene, s_spheres, reinterpret_cast<uint64_t *>(smem_raw));
+    const float4 *s_scan = s_spheres, *s_exact = s_spheres + a.scene.n_pad;
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_tiles = (w.n_slots + 32 * R - 1) / (32 * R);
+    uint32_t nrays = 0;
+    for (uint32_t tile = warp; tile < n_tiles; tile += warps) {
+        f3 o[R], d[R];
+        float t[R];
+        int hit[R];
+        bool live[R];
+        bool any_live = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const uint32_t slot = tile * (32 * R) + r * 32 + lane;
+            live[r] = slot < w.n_slots && w.meta[slot].x != kDead;
+            o[r] = mk3(0.0f, 1.0e18f, 0.0f); d[r] = mk3(0.0f, 0.0f, 0.0f);   // retired slots scan a ray that passes no filter
+            if (live[r]) {
+                const float4 ro = w.ray_o[slot], rd = w.ray_d[slot];
+                o[r] = mk3(ro.x, ro.y, ro.z); d[r] = mk3(rd.x, rd.y, rd.z);
+            }
+            t[r] = kTMax; hit[r] = -1;
+            any_live |= live[r];
+        }
+        if (!__any_sync(kFull, any_live)) continue;
+        scan_multi<R, (R >= 4 ? 4 : 8)>(s_scan, s_exact, a.scene.n_pad, o, d, kTMin, t, hit);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const uint32_t slot = tile * (32 * R) + r * 32 + lane;
+            int cls = -1;
+            if (live[r]) {
+                ++nrays;
+                w.hit_t[slot] = t[r];
+                w.hit_idx[slot] = hit[r];
+                cls = hit[r] < 0 ? 0 : 1 + __ldg(a.scene.kind + hit[r]);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {          // ballot + popc compaction: one atomic per warp per class
+                const unsigned m = __ballot_sync(kFull, cls == c);
+                if (m) {
+                    const int leader = __ffs(m) - 1;
+                    unsigned base = 0;
+                    if ((int)lane == leader) base = atomicAdd(&w.counters[c], (unsigned)__popc(m));
+                    base = __shfl_sync(kFull, base, leader);
+                    if (cls == c) w.queue[(size_t)c * w.n_slots + base + __popc(m & ((1u << lane) - 1u))] = slot;
+                }
+            }
+        }
+    }
+    unsigned long long total = nrays;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(kFull, total, off);
+    if (lane == 0 && total) atomicAdd(a.num_rays, total);
+}
+
+// color() + (on path end) accumulate, next sample / next unit, next primary ray -- class by class.
+__global__ void __launch_bounds__(256) wf_shade(const __grid_constant__ RenderArgs a, const __grid_constant__ WfState w)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t n0 = w.counters[0], n1 = w.counters[1], n2 = w.counters[2], n3 = w.counters[3];
+    // each class is padded to a multiple of 32 entries so that a warp never mixes classes
+    const uint32_t p0 = (n0 + 31) & ~31u, p1 = (n1 + 31) & ~31u, p2 = (n2 + 31) & ~31u, p3 = (n3 + 31) & ~31u;
+    const uint32_t total = p0 + p1 + p2 + p3;
+    uint32_t alive_count = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        uint32_t c, j;
+        if (i < p0) { c = 0; j = i; }
+        else if (i < p0 + p1) { c = 1; j = i - p0; }
+        else if (i < p0 + p1 + p2) { c = 2; j = i - p0 - p1; }
+        else { c = 3; j = i - p0 - p1 - p2; }
+        const uint32_t n_c = c == 0 ? n0 : c == 1 ? n1 : c == 2 ? n2 : n3;
+        const bool valid = j < n_c;
+        bool ended = false, alive = false;
+        uint32_t slot = 0, unit = 0;
+        int s = 0, depth = 0;
+        f3 o = mk3(0, 0, 0), d = mk3(0, 0, 0), thr = mk3(1, 1, 1), acc = mk3(0, 0, 0);
+        Rng rng; rng.key = 0; rng.ctr = 0;
+        if (valid) {
+            slot = w.queue[(size_t)c * w.n_slots + j];
+            const float4 ro = w.ray_o[slot], rd = w.ray_d[slot], th = w.thr[slot];
+            const uint4 m = w.meta[slot];
+            o = mk3(ro.x, ro.y, ro.z); d = mk3(rd.x, rd.y, rd.z); thr = mk3(th.x, th.y, th.z); depth = __float_as_int(th.w);
+            unit = m.x; s = (int)m.y; rng.key = m.z; rng.ctr = m.w;
+            const int hit = w.hit_idx[slot];
+            const float4 e = hit >= 0 ? __ldg(a.scene.exact + hit) : make_float4(0, 0, 0, 0);
+            f3 contrib;
+            ended = shade_step(a, hit, w.hit_t[slot], e, o, d, thr, depth, rng, contrib);
+            alive = true;
+            if (ended) {
+                const float4 ac = w.acc[slot];
+                acc = add3(mk3(ac.x, ac.y, ac.z), contrib);
+                ++s;
+            }
+        }
+        // path ended: next sample of the unit, or store the unit and take the next one (warp-aggregated atomic)
+        uint32_t pixel; float fx, fy; int s0, s_end;
+        bool want_unit = false;
+        if (ended) {
+            unit_begin(a, unit, pixel, fx, fy, s0, s_end);
+            if (s == s_end) {
+                a.partial[unit] = make_float4(acc.x, acc.y, acc.z, 0.0f);
+                want_unit = true;
+            }
+        }
+        const unsigned need = __ballot_sync(kFull, want_unit);
+        if (need) {
+            const int leader = __ffs(need) - 1;
+            unsigned base = 0;
+            if ((int)lane == leader) base = atomicAdd(a.unit_counter, (unsigned)__popc(need));
+            base = __shfl_sync(kFull, base, leader);
+            if (want_unit) {
+                unit = base + __popc(need & ((1u << lane) - 1u));
+                acc = mk3(0, 0, 0);
+                if (unit < a.n_units) unit_begin(a, unit, pixel, fx, fy, s, s_end);
+                else { alive = false; unit = kDead; }
+            }
+        }
+        if (valid) {
+            if (ended && alive) {
+                primary_ray(a, pixel, fx, fy, s, rng, o, d);
+                thr = mk3(1, 1, 1);
+                depth = 0;
+            }
+            if (ended) w.acc[slot] = make_float4(acc.x, acc.y, acc.z, 0.0f);
+            if (alive) wf_store_path(w, slot, o, d, thr, depth, unit, s, rng);
+            else w.meta[slot] = make_uint4(kDead, 0, 0, 0);
+            alive_count += alive ? 1u : 0u;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) alive_count += __shfl_xor_sync(kFull, alive_count, off);
+    if (lane == 0 && alive_count) atomicAdd(&w.counters[4], alive_count);
+}
+
+// loop control: one thread.  (handle == 0: host-driven loop, the flag is read back by the host instead)
+__global__ void wf_decide(const __grid_constant__ WfState w, cudaGraphConditionalHandle handle, uint32_t *host_flag)
+{
+    const uint32_t alive = w.counters[4];
+    for (int k = 0; k < 5; ++k) w.counters[k] = 0;
+    w.counters[5] += 1;
+    if (handle) cudaGraphSetConditional(handle, alive ? 1u : 0u);
+    if (host_flag) *host_flag = alive;
+}
+
+#define R1_WF_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return (int)e_; } while (0)
+
+inline uint32_t wavefront_slots(uint32_t n_units, int sm_count)
+{
+    // a multiple of one full wave of wf_intersect (SMs x warps x 32 lanes x R rays) so that every warp gets the same number of tiles
+    const uint64_t wave = (uint64_t)sm_count * kWfThreads * kWfRays;
+    uint64_t slots = wave * 8;
+    const uint64_t need = ((uint64_t)n_units + 32 * kWfRays - 1) / (32 * kWfRays) * (32 * kWfRays);
+    if (slots > need) slots = need;
+    return (uint32_t)slots;
+}
+
+// returns a cudaError_t (0 = ok).  Asynchronous on `stream` (graph mode); the unit counter must already be zeroed.
+inline int wavefront_render(WavefrontBuffers &b, const RenderArgs &a, int sm_count, cudaStream_t stream, uint32_t *launches)
 {
     *launches = 0;
-    return (int)cudaErrorNotSupported;
+    WfState w;
+    w.n_slots = wavefront_slots(a.n_units, sm_count);
+    const size_t n = w.n_slots;
+    const size_t bytes = n * (16 * 4 + 16 + 4 + 4 + 16) + 64 + 256;
+    if (bytes > b.pool_bytes) {
+        if (b.pool) cudaFree(b.pool);
+        b.pool = nullptr; b.pool_bytes = 0;
+        R1_WF_CUDA(cudaMalloc(&b.pool, bytes));
+        b.pool_bytes = bytes;
+    }
+    unsigned char *p = static_cast<unsigned char *>(b.pool);
+    w.ray_o = reinterpret_cast<float4 *>(p); p += n * 16;
+    w.ray_d = reinterpret_cast<float4 *>(p); p += n * 16;
+    w.thr = reinterpret_cast<float4 *>(p); p += n * 16;
+    w.acc = reinterpret_cast<float4 *>(p); p += n * 16;
+    w.meta = reinterpret_cast<uint4 *>(p); p += n * 16;
+    w.queue = reinterpret_cast<uint32_t *>(p); p += n * 16;
+    w.hit_t = reinterpret_cast<float *>(p); p += n * 4;
+    w.hit_idx = reinterpret_cast<int32_t *>(p); p += n * 4;
+    w.counters = reinterpret_cast<uint32_t *>(p);
+
+    b.d_iterations = w.counters + 5;
+    R1_WF_CUDA(cudaMemsetAsync(w.counters, 0, 64, stream));
+    const int init_grid = (int)std::min<size_t>((n + 255) / 256, (size_t)sm_count * 8);
+    wf_init<<<init_grid, 256, 0, stream>>>(a, w);
+    R1_WF_CUDA(cudaGetLastError());
+    *launches += 1;
+
+    const size_t smem = 16 + (size_t)a.scene.n_pad * 32;
+    R1_WF_CUDA(cudaFuncSetAttribute(wf_intersect<kWfRays>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t n_tiles = (w.n_slots + 32 * kWfRays - 1) / (32 * kWfRays);
+    const int igrid = (int)std::min<uint32_t>((uint32_t)sm_count, (n_tiles * 32 + kWfThreads - 1) / kWfThreads);
+    const int sgrid = sm_count * 8;
+
+    // the loop as a CUDA-graph WHILE node: intersect -> shade -> decide, repeated on the device until no slot is alive
+    if (b.exec) {  // the previous render's graph may still be running on this stream
+        R1_WF_CUDA(cudaStreamSynchronize(stream));
+        cudaGraphExecDestroy(b.exec);
+        b.exec = nullptr;
+    }
+    cudaGraph_t graph = nullptr;
+    R1_WF_CUDA(cudaGraphCreate(&graph, 0));
+    cudaGraphConditionalHandle handle;
+    R1_WF_CUDA(cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault));
+    cudaGraphNodeParams cond = { cudaGraphNodeTypeConditional };
+    cond.conditional.handle = handle;
+    cond.conditional.type = cudaGraphCondTypeWhile;
+    cond.conditional.size = 1;
+    cudaGraphNode_t node;
+    R1_WF_CUDA(cudaGraphAddNode(&node, graph, nullptr, 0, &cond));
+    cudaGraph_t body = cond.conditional.phGraph_out[0];
+    cudaStream_t cap;
+    R1_WF_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+    R1_WF_CUDA(cudaStreamBeginCaptureToGraph(cap, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+    wf_intersect<kWfRays><<<igrid, kWfThreads, smem, cap>>>(a, w);
+    wf_shade<<<sgrid, 256, 0, cap>>>(a, w);
+    wf_decide<<<1, 1, 0, cap>>>(w, handle, nullptr);
+    R1_WF_CUDA(cudaStreamEndCapture(cap, nullptr));
+    R1_WF_CUDA(cudaStreamDestroy(cap));
+    R1_WF_CUDA(cudaGraphInstantiate(&b.exec, graph, 0));
+    R1_WF_CUDA(cudaGraphDestroy(graph));
+    R1_WF_CUDA(cudaGraphLaunch(b.exec, stream));
+    // 3 kernels per loop iteration; the iteration count lives on the device (d_iterations) and is read by r1_render_wait
+    *launches += 0;
+    return 0;
 }
 
 }  // namespace r1

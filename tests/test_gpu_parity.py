@@ -203,6 +203,17 @@ def test_full_size_default_workload(r1, scenes, ref_stats, name):
     assert res.launches == 2 and res.kernel_ms > 0 and res.trace_ms <= res.kernel_ms
 
 
+@pytest.mark.parametrize("name", SCENES)
+def test_wavefront_full_size_matches_megakernel(r1, scenes, name):
+    """the wavefront variant (queues compacted with ballot + popc, CUDA-graph loop) renders the same bytes at full size"""
+    a, ra = scenes[name].render(1280, 720, 32)
+    b, rb = scenes[name].render(1280, 720, 32, variant=r1.VARIANT_WAVEFRONT)
+    assert np.array_equal(a, b) and ra.num_rays == rb.num_rays
+    part, rp = scenes[name].render(1280, 720, 32, variant=r1.VARIANT_WAVEFRONT, rank=1, world=4)
+    rows = [r1.global_row(lr, 8, 1, 4) for lr in range(part.shape[0])]
+    assert np.array_equal(part, a[rows])
+
+
 def test_synth4096_against_oracle_render(r1, scenes, oracle):
     """config 5: no reference image exists (MAX_SPHERES = 1024 in the reference, rayweek1.cpp:174) -> oracle render."""
     w, h, spp = 96, 54, 64
@@ -227,6 +238,12 @@ def test_bitwise_invariance(r1, scenes):
     assert np.array_equal(base, scal) and rs.num_rays == r0.num_rays
     more, rm = s.render(w, h, spp, blocks_per_sm=2)
     assert np.array_equal(base, more) and rm.num_rays == r0.num_rays
+    for threads in (512, 768):
+        alt, ra = s.render(w, h, spp, threads=threads)
+        assert np.array_equal(base, alt) and ra.num_rays == r0.num_rays
+    wave, rw = s.render(w, h, spp, variant=r1.VARIANT_WAVEFRONT)
+    assert np.array_equal(base, wave) and rw.num_rays == r0.num_rays
+    assert rw.launches > 5
     for world in (2, 3, 8):
         parts, rays = [], 0
         for rank in range(world):
@@ -298,3 +315,19 @@ def test_drop_in_executable(r1, tmp_path):
         tok = txt.split("|")
         assert tok[0] == "b200" and tok[1].endswith("s") and int(tok[2]) > 1280 * 720 * 4 and tok[3].endswith(" mrays/s") and tok[4] == ""
         assert os.path.getsize(tmp_path / ("out_%s.tga" % name)) == 18 + 1280 * 720 * 3
+
+
+def test_in_process_multi_gpu_matches_single_gpu(r1, tmp_path):
+    """--gpus 2 in ONE process (NCCL gather + reduce, rays1_host.cpp:render_multi) renders the same bytes and ray count."""
+    if r1.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    outs = {}
+    for g in (1, 2):
+        d = tmp_path / ("g%d" % g)
+        d.mkdir()
+        out = subprocess.run([r1.EXE_PATH, "-w", "--gpus", str(g), "--scene", "large", "--spp", "16", "--width", "640", "--height", "360"],
+                             cwd=d, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr
+        rays = [l for l in out.stdout.splitlines() if l.startswith("total rays:")][0]
+        outs[g] = (open(d / "out_large.tga", "rb").read(), rays)
+    assert outs[1] == outs[2]

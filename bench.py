@@ -127,7 +127,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="large", choices=sorted(WORKLOADS))
-    ap.add_argument("--variant", default="mega", choices=["mega", "wavefront", "scalar"])
+    ap.add_argument("--variant", default="mega", choices=["mega", "wavefront", "scalar", "coop"])
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work per reference step / baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--threads", type=int, default=0, help="threads per persistent CTA (512/768/1024; 0 = library default)")
@@ -191,7 +191,7 @@ def main():
     scene = r1.create_scene(scene_name, commit=False)
     r1._check(r1.lib.r1_scene_commit(scene.handle, local_rank), "r1_scene_commit")
     n_real = r1.REAL_SPHERES[scene_name]
-    n_pad = (scene.count() + 7) // 8 * 8
+    n_pad = (scene.count() + 15) // 16 * 16
 
     my_rows = r1.local_rows(H, row_tile, rank, world)
     max_rows = r1d.max_local_rows(H, row_tile, world)
@@ -233,7 +233,8 @@ def main():
             total_ms += e0.elapsed_time(e1)
             waited = scene.render_wait(local_rank)
             trace_ms += waited.trace_ms
-            n_l += waited.launches - (n_l if world == 1 else n_l - 1)  # wavefront: the loop's kernels are counted on the device
+            n_l = waited.launches + (1 if (world > 1 and rank == 0) else 0)  # trace kernel(s) + resolve (+ de-interleave); the
+            #                                                                 wavefront's loop iterations are counted on the device
             total_rays += int(d_rays.item()) if rank == 0 else 0  # for N > 1 the reduced total lives on rank 0
             launches += n_l
     clocks = sampler.end() if sampler else None
@@ -286,7 +287,8 @@ def main():
     sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
     peak_nominal = sm_count * 128 * 2 * NOMINAL_SM_MHZ * 1e6 / 1e12
     achieved = total_rays * f_ray / (ms_trace * 1e-3) / 1e12 / world  # per GPU
-    n_chunks = (SPP + max(8, (SPP + 15) // 16) - 1) // max(8, (SPP + 15) // 16)
+    spu = max(4, (SPP + 63) // 64)
+    n_chunks = (SPP + spu - 1) // spu
     hbm_bytes = W * H * (n_chunks * 16 * 2 + 3) + n_pad * 32 * sm_count
     roofline = {"bound": "fp32_fma", "kernel": "r1::megakernel" if args.variant != "wavefront" else "r1::wf_intersect + wf_shade (graph loop)", "achieved": achieved,
                 "peak": peak_meas, "unit": "TFLOP/s", "frac": achieved / peak_meas,

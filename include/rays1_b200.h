@@ -36,9 +36,11 @@ enum { R1_MAT_NONE = -1, R1_MAT_LAMBERT = 0, R1_MAT_METAL = 1, R1_MAT_DIELECTRIC
 
 /* Kernel variants measured against each other (north_star (2)). */
 enum {
-    R1_VARIANT_MEGAKERNEL = 0, /* persistent threads, per-lane path state machine, packed f32x2 scan */
-    R1_VARIANT_WAVEFRONT = 1,  /* generate / intersect / shade kernels over compacted ray queues */
-    R1_VARIANT_MEGAKERNEL_SCALAR = 2 /* same megakernel with a scalar FFMA scan (A/B for the packed scan) */
+    R1_VARIANT_MEGAKERNEL = 0, /* persistent threads, per-lane path state machine, per-lane packed f32x2 scan (fastest; default) */
+    R1_VARIANT_WAVEFRONT = 1,  /* generate / intersect / shade kernels over compacted ray queues, CUDA-graph WHILE loop */
+    R1_VARIANT_MEGAKERNEL_SCALAR = 2, /* A/B: megakernel with a per-lane scalar FFMA scan */
+    R1_VARIANT_MEGAKERNEL_COOP = 3    /* A/B: megakernel with the warp-cooperative scan (quads share sphere loads, candidates
+                                         resolved through a per-warp shared-memory queue) */
 };
 
 typedef struct r1_scene r1_scene; /* opaque: host SoA + per-device buffers */

@@ -135,8 +135,9 @@ int get_ctx(r1_scene *scene, DeviceCtx **out, int device = -1)
     return R1_OK;
 }
 
-// samples per unit: a function of spp ONLY (see RenderArgs) -- at most 16 chunks per pixel, at least 8 samples each
-int samples_per_unit(int spp) { return std::max(8, (spp + 15) / 16); }
+// samples per unit: a function of spp ONLY (see RenderArgs) -- at most 64 chunks per pixel, at least 4 samples each.
+// Small units keep the tail short: a lane needs ~0.08 ms per sample on the large scene, and a render on 8 GPUs lasts 16 ms.
+int samples_per_unit(int spp) { return std::max(4, (spp + 63) / 64); }
 
 struct Partition { int local_rows; uint32_t npix_local; };
 
@@ -150,14 +151,15 @@ Partition partition(int width, int height, int row_tile, int rank, int world)
 
 // One persistent CTA per SM; kThreads = 512 / 768 / 1024 (4 / 6 / 8 warps per scheduler; ptxas fits 96 / 76 / 64 registers
 // without spills).  Shared memory = 16 + n_pad * 32 bytes.
-constexpr int kDefaultThreads = 1024;
+constexpr int kDefaultThreads = 1024;     // per-lane scans: 64 registers
+constexpr int kDefaultThreadsCoop = 512;  // cooperative scan: 4 rays per lane in flight, 127 registers
 
-template <bool kPacked, bool kStaged, int kThreads>
+template <int kScan, bool kStaged, int kThreads>
 int launch_megakernel_t(int sm_count, const r1::RenderArgs &args, const r1_render_params &prm, cudaStream_t stream)
 {
     constexpr int kBlocks = 1;
-    auto kern = r1::megakernel<kPacked, kStaged, kThreads, kBlocks>;
-    const size_t smem = kStaged ? 16 + (size_t)args.scene.n_pad * 32 : 0;
+    auto kern = r1::megakernel<kScan, kStaged, kThreads, kBlocks>;
+    const size_t smem = 16 + (kStaged ? (size_t)args.scene.n_pad * 32 : 0) + (kScan == r1::kScanCoop ? sizeof(r1::WarpScratch) * (kThreads / 32) : 0);
     R1_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = sm_count * kBlocks;
     if (prm.blocks_per_sm > 0) grid = sm_count * prm.blocks_per_sm;
@@ -169,13 +171,13 @@ int launch_megakernel_t(int sm_count, const r1::RenderArgs &args, const r1_rende
     return R1_OK;
 }
 
-template <bool kPacked, bool kStaged>
+template <int kScan, bool kStaged>
 int launch_megakernel(int sm_count, const r1::RenderArgs &args, const r1_render_params &prm, cudaStream_t stream)
 {
-    const int threads = prm.threads > 0 ? prm.threads : kDefaultThreads;
-    if (threads == 512) return launch_megakernel_t<kPacked, kStaged, 512>(sm_count, args, prm, stream);
-    if (threads == 768) return launch_megakernel_t<kPacked, kStaged, 768>(sm_count, args, prm, stream);
-    if (threads == 1024) return launch_megakernel_t<kPacked, kStaged, 1024>(sm_count, args, prm, stream);
+    const int threads = prm.threads > 0 ? prm.threads : (kScan == r1::kScanCoop ? kDefaultThreadsCoop : kDefaultThreads);
+    if (threads == 512) return launch_megakernel_t<kScan, kStaged, 512>(sm_count, args, prm, stream);
+    if (threads == 768) return launch_megakernel_t<kScan, kStaged, 768>(sm_count, args, prm, stream);
+    if (threads == 1024) return launch_megakernel_t<kScan, kStaged, 1024>(sm_count, args, prm, stream);
     return fail(R1_ERR_ARG, "threads must be 512, 768 or 1024 (got %d)", threads);
 }
 
@@ -185,7 +187,7 @@ int validate(const r1_render_params *p)
     if (p->width <= 0 || p->height <= 0 || p->spp <= 0 || p->max_bounces < 0) return fail(R1_ERR_ARG, "width/height/spp must be > 0, max_bounces >= 0");
     if (p->world <= 0 || p->rank < 0 || p->rank >= p->world) return fail(R1_ERR_ARG, "bad rank/world %d/%d", p->rank, p->world);
     if ((uint64_t)p->width * (uint64_t)p->height > (1ull << 31)) return fail(R1_ERR_ARG, "image too large");
-    if (p->variant < 0 || p->variant > 2) return fail(R1_ERR_ARG, "unknown variant %d", p->variant);
+    if (p->variant < 0 || p->variant > 3) return fail(R1_ERR_ARG, "unknown variant %d", p->variant);
     return R1_OK;
 }
 
@@ -316,7 +318,7 @@ int r1_scene_commit(r1_scene *scene, int device)
     c.device = device;
 
     const int n = (int)scene->cx.size();
-    const int n_pad = (n + 7) / 8 * 8;  // the reference's own padding (SIMD_WIDTH, rayweek1.cpp:38, 575)
+    const int n_pad = (n + 15) / 16 * 16;  // one scan supergroup = 16 spheres (the reference pads to SIMD_WIDTH = 8, rayweek1.cpp:575)
     const float inf = std::numeric_limits<float>::infinity();
     // host image of the device block: [scan n_pad f4 | exact n_pad f4 | mat n_pad f4 | inv_radius n_pad f | kind n_pad i32]
     const size_t bytes = (size_t)n_pad * (16 + 16 + 16 + 4 + 4);
@@ -328,11 +330,12 @@ int r1_scene_commit(r1_scene *scene, int device)
     int32_t *kind = reinterpret_cast<int32_t *>(inv_r + n_pad);
     for (int i = 0; i < n_pad; ++i) {
         const bool real = i < n && scene->inv_radius[i] != 0;  // rayweek1.cpp:288-292: inv_radius == 0 spheres never hit
-        const int g = i / 4, k = i % 4;
-        scan[16 * g + 0 + k] = real ? -scene->cx[i] : 0.0f;
-        scan[16 * g + 4 + k] = real ? -scene->cy[i] : 0.0f;
-        scan[16 * g + 8 + k] = real ? -scene->cz[i] : 0.0f;
-        scan[16 * g + 12 + k] = real ? -(scene->radius_sq[i] * (1.0f + 1.0f / 256.0f)) : inf;
+        // supergroup layout (r1_device.cuh): group g = i / 4 at float4 index (g >> 2) * 16 + (g & 3); cy / cz / r2f at +4 / +8 / +12
+        const int g = i / 4, k = i % 4, f4 = (g >> 2) * 16 + (g & 3);
+        scan[4 * (f4 + 0) + k] = real ? -scene->cx[i] : 0.0f;
+        scan[4 * (f4 + 4) + k] = real ? -scene->cy[i] : 0.0f;
+        scan[4 * (f4 + 8) + k] = real ? -scene->cz[i] : 0.0f;
+        scan[4 * (f4 + 12) + k] = real ? -(scene->radius_sq[i] * (1.0f + 1.0f / 256.0f)) : inf;
         kind[i] = R1_MAT_NONE;
         if (i < n) {
             exact[i] = make_float4(scene->cx[i], scene->cy[i], scene->cz[i], scene->radius_sq[i]);
@@ -350,6 +353,7 @@ int r1_scene_commit(r1_scene *scene, int device)
     c.dev.inv_radius = reinterpret_cast<float *>(d4 + 3 * (size_t)n_pad);
     c.dev.kind = reinterpret_cast<const int32_t *>(c.dev.inv_radius + n_pad);
     c.dev.n_pad = n_pad;
+    c.dev.n8 = (n + 7) / 8 * 8;
     c.dev.n_real = n;
     c.dev.cam = scene->cam;
     scene->current = device;
@@ -415,7 +419,7 @@ int r1_render_device(r1_scene *scene, const r1_render_params *params, void *d_rg
     const uint64_t n_units = (uint64_t)a.npix_local * (uint64_t)a.n_chunks;
     if (n_units >= (1ull << 32) - (1ull << 24)) return fail(R1_ERR_LIMIT, "too many work units (%llu)", (unsigned long long)n_units);
     a.n_units = (uint32_t)n_units;
-    a.seed = prm.seed;
+    a.seed = r1::Rng::seed_hash(prm.seed);
     a.inv_w = 1.0f / prm.width; a.inv_h = 1.0f / prm.height;  // rayweek1.cpp:746
     a.inv_spp = (float)(1.0f / prm.spp);                       // rayweek1.cpp:765
     a.magic_npix = r1::div_magic(a.npix_local);
@@ -443,11 +447,12 @@ int r1_render_device(r1_scene *scene, const r1_render_params *params, void *d_rg
             if (rc) return fail(R1_ERR_CUDA, "wavefront: %s", cudaGetErrorString((cudaError_t)rc));
             x.last_launches += launches;
         } else {
-            const bool packed = prm.variant == R1_VARIANT_MEGAKERNEL;
-            if (packed && staged) rc = launch_megakernel<true, true>(x.sm_count, a, prm, stream);
-            else if (packed) rc = launch_megakernel<true, false>(x.sm_count, a, prm, stream);
-            else if (staged) rc = launch_megakernel<false, true>(x.sm_count, a, prm, stream);
-            else rc = launch_megakernel<false, false>(x.sm_count, a, prm, stream);
+            if (prm.variant == R1_VARIANT_MEGAKERNEL) rc = staged ? launch_megakernel<r1::kScanLanePacked, true>(x.sm_count, a, prm, stream)
+                                                                  : launch_megakernel<r1::kScanLanePacked, false>(x.sm_count, a, prm, stream);
+            else if (prm.variant == R1_VARIANT_MEGAKERNEL_COOP) rc = staged ? launch_megakernel<r1::kScanCoop, true>(x.sm_count, a, prm, stream)
+                                                                            : launch_megakernel<r1::kScanCoop, false>(x.sm_count, a, prm, stream);
+            else rc = staged ? launch_megakernel<r1::kScanLaneScalar, true>(x.sm_count, a, prm, stream)
+                             : launch_megakernel<r1::kScanLaneScalar, false>(x.sm_count, a, prm, stream);
             if (rc) return rc;
             x.last_launches += 1;
         }
@@ -558,17 +563,17 @@ int r1_trace_rays(r1_scene *scene, int n, const float *org, const float *dir, fl
     DevBuf d_org, d_dir, d_idx, d_t, d_p, d_n;
     R1_TRY(d_org.upload(org, (size_t)n * 12)); R1_TRY(d_dir.upload(dir, (size_t)n * 12));
     R1_TRY(d_idx.alloc((size_t)n * 4)); R1_TRY(d_t.alloc((size_t)n * 4)); R1_TRY(d_p.alloc((size_t)n * 12)); R1_TRY(d_n.alloc((size_t)n * 12));
-    const size_t smem = 16 + (size_t)cp->dev.n_pad * 32;
+    const size_t smem = 16 + (size_t)cp->dev.n_pad * 32 + sizeof(r1::WarpScratch) * 4;
     const int grid = (n + 127) / 128;
-    if (variant == R1_VARIANT_MEGAKERNEL_SCALAR) {
-        R1_CUDA(cudaFuncSetAttribute(r1::trace_rays_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        r1::trace_rays_kernel<false><<<grid, 128, smem>>>(cp->dev, n, d_org.as<float>(), d_dir.as<float>(), t_min, t_max, d_idx.as<int32_t>(),
-                                                          d_t.as<float>(), d_p.as<float>(), d_n.as<float>());
-    } else {
-        R1_CUDA(cudaFuncSetAttribute(r1::trace_rays_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        r1::trace_rays_kernel<true><<<grid, 128, smem>>>(cp->dev, n, d_org.as<float>(), d_dir.as<float>(), t_min, t_max, d_idx.as<int32_t>(),
-                                                         d_t.as<float>(), d_p.as<float>(), d_n.as<float>());
-    }
+    auto launch = [&](auto kern) -> int {
+        R1_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 128, smem>>>(cp->dev, n, d_org.as<float>(), d_dir.as<float>(), t_min, t_max, d_idx.as<int32_t>(), d_t.as<float>(), d_p.as<float>(),
+                                  d_n.as<float>());
+        return R1_OK;
+    };
+    if (variant == R1_VARIANT_MEGAKERNEL_SCALAR) R1_TRY(launch(r1::trace_rays_kernel<r1::kScanLaneScalar>));
+    else if (variant == R1_VARIANT_MEGAKERNEL_COOP) R1_TRY(launch(r1::trace_rays_kernel<r1::kScanCoop>));
+    else R1_TRY(launch(r1::trace_rays_kernel<r1::kScanLanePacked>));
     R1_CUDA(cudaGetLastError());
     R1_CUDA(cudaDeviceSynchronize());
     R1_TRY(d_idx.download(index, (size_t)n * 4)); R1_TRY(d_t.download(t, (size_t)n * 4));

@@ -22,7 +22,7 @@ struct RenderArgs {
     int32_t rank, world, row_tile;
     uint32_t npix_local, n_units;
     int32_t samples_per_unit, n_chunks;
-    uint32_t seed;
+    uint32_t seed;                   // Rng::seed_hash(global seed)
     float inv_w, inv_h, inv_spp;
     uint64_t magic_npix, magic_width;  // floor(2^64 / d) + 1: exact n / d for 32-bit n via one 64-bit mul-high (0 when d == 1)
 };
@@ -118,7 +118,10 @@ __device__ __forceinline__ bool shade_step(const RenderArgs &a, int hit, float t
 // Persistent CTAs; every lane runs  loop { take a unit | start a sample | SCAN | shade }  so that all 32 lanes enter
 // every scan with a live ray and divergence is confined to the short fetch / generate / shade steps.
 // Replaces render_tile + color + TileRenderScheduler (rayweek1.cpp:722-842, 515-536).
-template <bool kPacked, bool kStaged, int kThreads, int kBlocksPerSM>
+// kScan: which Hitable::hit implementation the lanes run
+enum ScanKind { kScanCoop = 0, kScanLanePacked = 1, kScanLaneScalar = 2 };
+
+template <int kScan, bool kStaged, int kThreads, int kBlocksPerSM>
 __global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel(const __grid_constant__ RenderArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -134,6 +137,8 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel(const __gri
     }
     const int n_pad = a.scene.n_pad;
     const unsigned lane = threadIdx.x & 31u;
+    // per-warp scratch of the cooperative scan, behind the staged spheres
+    WarpScratch *ws = reinterpret_cast<WarpScratch *>(smem_raw + 16 + (kStaged ? (size_t)n_pad * 32 : 0)) + (threadIdx.x >> 5);
 
     bool active = false, exhausted = false, need_primary = false;
     uint32_t unit = 0, pixel = 0, nrays = 0;
@@ -178,7 +183,8 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel(const __gri
         // -- Hitable::hit (rayweek1.cpp:152-339): uniform trip count, all lanes
         float t = kTMax;
         int hit = -1;
-        scan<kPacked>(s_scan, s_exact, n_pad, o, d, kTMin, t, hit);
+        if (kScan == kScanCoop) scan_coop<(kThreads <= 512 ? 2 : 1)>(*ws, s_scan, s_exact, n_pad, o, d, kTMin, kTMax, t, hit);
+        else scan<kScan == kScanLanePacked>(s_scan, s_exact, a.scene.n8, o, d, kTMin, t, hit);
 
         // -- color() body (rayweek1.cpp:515-536)
         if (active) {
@@ -238,19 +244,23 @@ __global__ void __launch_bounds__(256) deinterleave_rows(const uint8_t *gathered
 }
 
 // ------------------------------------------------------------------------------------------------ parity kernels
-template <bool kPacked>
+template <int kScan>
 __global__ void __launch_bounds__(128) trace_rays_kernel(const __grid_constant__ DevScene sc, int n, const float *org, const float *dir,
                                                          float t_min, float t_max, int32_t *index, float *t_out, float *p_out, float *n_out)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4 *s_spheres = reinterpret_cast<float4 *>(smem_raw + 16);
     stage_spheres(sc, s_spheres, reinterpret_cast<uint64_t *>(smem_raw));
+    WarpScratch *ws = reinterpret_cast<WarpScratch *>(smem_raw + 16 + (size_t)sc.n_pad * 32) + (threadIdx.x >> 5);
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const f3 o = mk3(org[3 * k], org[3 * k + 1], org[3 * k + 2]), d = mk3(dir[3 * k], dir[3 * k + 1], dir[3 * k + 2]);
+    const bool live = k < n;                               // the whole warp takes part in the cooperative scan
+    f3 o = mk3(0.0f, 1.0e18f, 0.0f), d = mk3(0.0f, 0.0f, 0.0f);
+    if (live) { o = mk3(org[3 * k], org[3 * k + 1], org[3 * k + 2]); d = mk3(dir[3 * k], dir[3 * k + 1], dir[3 * k + 2]); }
     float t = t_max;
     int hit = -1;
-    scan<kPacked>(s_spheres, s_spheres + sc.n_pad, sc.n_pad, o, d, t_min, t, hit);
+    if (kScan == kScanCoop) scan_coop<2>(*ws, s_spheres, s_spheres + sc.n_pad, sc.n_pad, o, d, t_min, t_max, t, hit);
+    else scan<kScan == kScanLanePacked>(s_spheres, s_spheres + sc.n_pad, sc.n8, o, d, t_min, t, hit);
+    if (!live) return;
     f3 p = mk3(0, 0, 0), nrm = mk3(0, 0, 0);
     if (hit >= 0) hit_finalise(s_spheres[sc.n_pad + hit], sc.inv_radius[hit], o, d, t, p, nrm);
     index[k] = hit;
@@ -289,7 +299,7 @@ __global__ void rng_kernel(uint32_t pixel, uint32_t sample, uint32_t seed, int n
 {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         Rng rng;
-        rng.seed(pixel, sample, seed);
+        rng.seed(pixel, sample, Rng::seed_hash(seed));
         for (int i = 0; i < n; ++i) out[i] = rng.next();
     }
 }

@@ -3,7 +3,7 @@
 //
 //   wf_init       every slot takes a unit and generates its first primary ray
 //   loop (a CUDA-graph WHILE node: the host never waits inside the loop)
-//     wf_intersect  all live slots: Hitable::hit with R rays per lane sharing each sphere load; classifies each slot
+//     wf_intersect  the compacted list of live slots: Hitable::hit with R rays per lane sharing each sphere load; classifies each slot
 //                   (miss / lambertian / metal / dielectric) and appends it to that class's queue, compacted with
 //                   warp ballot + one atomic per warp per class
 //     wf_shade      walks the queues class by class, so a warp shades 32 rays of ONE material (or 32 misses, which also
@@ -14,6 +14,9 @@
 // partial sums.  State: 88 bytes per slot (SoA), ~2.4 M slots.
 #pragma once
 #include "r1_kernels.cuh"
+
+#include <cstdio>
+#include <cstdlib>
 
 namespace r1 {
 
@@ -30,7 +33,9 @@ struct WfState {
     float *hit_t;
     int32_t *hit_idx;
     uint32_t *queue;    // 4 classes x n_slots slot indices
-    uint32_t *counters; // [0..3] class queue lengths, [4] live slots after shade, [5] loop iterations so far
+    uint32_t *alive[2]; // compacted lists of live slots: intersect reads alive[parity], shade fills alive[parity ^ 1]
+    uint32_t *counters; // [0..3] class queue lengths, [4] live slots after shade, [5] loop iterations so far,
+                        // [6] parity, [7] length of alive[parity]
     uint32_t n_slots;
 };
 
@@ -59,7 +64,11 @@ __device__ __forceinline__ void wf_store_path(const WfState &w, uint32_t slot, f
 // slot i starts unit i (the unit counter is preset to min(n_slots, n_units))
 __global__ void __launch_bounds__(256) wf_init(const __grid_constant__ RenderArgs a, const __grid_constant__ WfState w)
 {
-    if (blockIdx.x == 0 && threadIdx.x == 0) *a.unit_counter = a.n_units < w.n_slots ? a.n_units : w.n_slots;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const uint32_t first = a.n_units < w.n_slots ? a.n_units : w.n_slots;
+        *a.unit_counter = first;
+        w.counters[7] = first;                              // slots 0 .. first-1 are alive, in order
+    }
     for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < w.n_slots; slot += gridDim.x * blockDim.x) {
         if (slot < a.n_units) {
             uint32_t pixel; float fx, fy; int s, s_end;
@@ -68,6 +77,7 @@ __global__ void __launch_bounds__(256) wf_init(const __grid_constant__ RenderArg
             primary_ray(a, pixel, fx, fy, s, rng, o, d);
             wf_store_path(w, slot, o, d, mk3(1, 1, 1), 0, slot, s, rng);
             w.acc[slot] = make_float4(0, 0, 0, 0);
+            w.alive[0][slot] = slot;
         } else {
             w.meta[slot] = make_uint4(kDead, 0, 0, 0);
         }
@@ -84,31 +94,32 @@ __global__ void __launch_bounds__(kWfThreads, 1) wf_intersect(const __grid_const
     const float4 *s_scan = s_spheres, *s_exact = s_spheres + a.scene.n_pad;
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t n_tiles = (w.n_slots + 32 * R - 1) / (32 * R);
+    const uint32_t n_alive = w.counters[7];
+    const uint32_t *alive = w.alive[w.counters[6] & 1u];
+    const uint32_t n_tiles = (n_alive + 32 * R - 1) / (32 * R);
     uint32_t nrays = 0;
     for (uint32_t tile = warp; tile < n_tiles; tile += warps) {
         f3 o[R], d[R];
         float t[R];
         int hit[R];
+        uint32_t slots[R];
         bool live[R];
-        bool any_live = false;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const uint32_t slot = tile * (32 * R) + r * 32 + lane;
-            live[r] = slot < w.n_slots && w.meta[slot].x != kDead;
-            o[r] = mk3(0.0f, 1.0e18f, 0.0f); d[r] = mk3(0.0f, 0.0f, 0.0f);   // retired slots scan a ray that passes no filter
+            const uint32_t i = tile * (32 * R) + r * 32 + lane;
+            live[r] = i < n_alive;
+            slots[r] = live[r] ? alive[i] : 0u;
+            o[r] = mk3(0.0f, 1.0e18f, 0.0f); d[r] = mk3(0.0f, 0.0f, 0.0f);   // lanes past the end scan a ray that passes no filter
             if (live[r]) {
-                const float4 ro = w.ray_o[slot], rd = w.ray_d[slot];
+                const float4 ro = w.ray_o[slots[r]], rd = w.ray_d[slots[r]];
                 o[r] = mk3(ro.x, ro.y, ro.z); d[r] = mk3(rd.x, rd.y, rd.z);
             }
             t[r] = kTMax; hit[r] = -1;
-            any_live |= live[r];
         }
-        if (!__any_sync(kFull, any_live)) continue;
-        scan_multi<R, (R >= 4 ? 4 : 8)>(s_scan, s_exact, a.scene.n_pad, o, d, kTMin, t, hit);
+        scan_multi<R, (R >= 4 ? 4 : 8)>(s_scan, s_exact, a.scene.n8, o, d, kTMin, t, hit);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const uint32_t slot = tile * (32 * R) + r * 32 + lane;
+            const uint32_t slot = slots[r];
             int cls = -1;
             if (live[r]) {
                 ++nrays;
@@ -143,7 +154,7 @@ __global__ void __launch_bounds__(256) wf_shade(const __grid_constant__ RenderAr
     // each class is padded to a multiple of 32 entries so that a warp never mixes classes
     const uint32_t p0 = (n0 + 31) & ~31u, p1 = (n1 + 31) & ~31u, p2 = (n2 + 31) & ~31u, p3 = (n3 + 31) & ~31u;
     const uint32_t total = p0 + p1 + p2 + p3;
-    uint32_t alive_count = 0;
+    uint32_t *next_alive = w.alive[(w.counters[6] & 1u) ^ 1u];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         uint32_t c, j;
         if (i < p0) { c = 0; j = i; }
@@ -206,12 +217,17 @@ __global__ void __launch_bounds__(256) wf_shade(const __grid_constant__ RenderAr
             if (ended) w.acc[slot] = make_float4(acc.x, acc.y, acc.z, 0.0f);
             if (alive) wf_store_path(w, slot, o, d, thr, depth, unit, s, rng);
             else w.meta[slot] = make_uint4(kDead, 0, 0, 0);
-            alive_count += alive ? 1u : 0u;
+        }
+        // live slots go to the next iteration's compacted list (ballot + popc, one atomic per warp)
+        const unsigned am = __ballot_sync(kFull, valid && alive);
+        if (am) {
+            const int leader = __ffs(am) - 1;
+            unsigned base = 0;
+            if ((int)lane == leader) base = atomicAdd(&w.counters[4], (unsigned)__popc(am));
+            base = __shfl_sync(kFull, base, leader);
+            if (valid && alive) next_alive[base + __popc(am & ((1u << lane) - 1u))] = slot;
         }
     }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) alive_count += __shfl_xor_sync(kFull, alive_count, off);
-    if (lane == 0 && alive_count) atomicAdd(&w.counters[4], alive_count);
 }
 
 // loop control: one thread.  (handle == 0: host-driven loop, the flag is read back by the host instead)
@@ -220,6 +236,8 @@ __global__ void wf_decide(const __grid_constant__ WfState w, cudaGraphConditiona
     const uint32_t alive = w.counters[4];
     for (int k = 0; k < 5; ++k) w.counters[k] = 0;
     w.counters[5] += 1;
+    w.counters[6] ^= 1u;
+    w.counters[7] = alive;
     if (handle) cudaGraphSetConditional(handle, alive ? 1u : 0u);
     if (host_flag) *host_flag = alive;
 }
@@ -243,7 +261,7 @@ inline int wavefront_render(WavefrontBuffers &b, const RenderArgs &a, int sm_cou
     WfState w;
     w.n_slots = wavefront_slots(a.n_units, sm_count);
     const size_t n = w.n_slots;
-    const size_t bytes = n * (16 * 4 + 16 + 4 + 4 + 16) + 64 + 256;
+    const size_t bytes = n * (16 * 4 + 16 + 4 + 4 + 16 + 8) + 64 + 256;
     if (bytes > b.pool_bytes) {
         if (b.pool) cudaFree(b.pool);
         b.pool = nullptr; b.pool_bytes = 0;
@@ -259,6 +277,8 @@ inline int wavefront_render(WavefrontBuffers &b, const RenderArgs &a, int sm_cou
     w.queue = reinterpret_cast<uint32_t *>(p); p += n * 16;
     w.hit_t = reinterpret_cast<float *>(p); p += n * 4;
     w.hit_idx = reinterpret_cast<int32_t *>(p); p += n * 4;
+    w.alive[0] = reinterpret_cast<uint32_t *>(p); p += n * 4;
+    w.alive[1] = reinterpret_cast<uint32_t *>(p); p += n * 4;
     w.counters = reinterpret_cast<uint32_t *>(p);
 
     b.d_iterations = w.counters + 5;
@@ -274,6 +294,37 @@ inline int wavefront_render(WavefrontBuffers &b, const RenderArgs &a, int sm_cou
     const int igrid = (int)std::min<uint32_t>((uint32_t)sm_count, (n_tiles * 32 + kWfThreads - 1) / kWfThreads);
     const int sgrid = sm_count * 8;
 
+    if (getenv("R1_WF_HOSTLOOP")) {
+        // debugging / per-kernel timing path: the same three kernels driven from the host (synchronous)
+        uint32_t *flag = nullptr;
+        R1_WF_CUDA(cudaMallocHost(&flag, sizeof(uint32_t)));
+        cudaEvent_t ev[4];
+        for (auto &e : ev) R1_WF_CUDA(cudaEventCreate(&e));
+        double ms_i = 0, ms_s = 0, ms_d = 0;
+        uint32_t iters = 0;
+        *flag = 1;
+        while (*flag) {
+            R1_WF_CUDA(cudaEventRecord(ev[0], stream));
+            wf_intersect<kWfRays><<<igrid, kWfThreads, smem, stream>>>(a, w);
+            R1_WF_CUDA(cudaEventRecord(ev[1], stream));
+            wf_shade<<<sgrid, 256, 0, stream>>>(a, w);
+            R1_WF_CUDA(cudaEventRecord(ev[2], stream));
+            wf_decide<<<1, 1, 0, stream>>>(w, 0, flag);
+            R1_WF_CUDA(cudaEventRecord(ev[3], stream));
+            R1_WF_CUDA(cudaStreamSynchronize(stream));
+            float t;
+            cudaEventElapsedTime(&t, ev[0], ev[1]); ms_i += t;
+            cudaEventElapsedTime(&t, ev[1], ev[2]); ms_s += t;
+            cudaEventElapsedTime(&t, ev[2], ev[3]); ms_d += t;
+            ++iters;
+        }
+        fprintf(stderr, "[r1 wavefront host loop] slots %u iterations %u: intersect %.2f ms, shade %.2f ms, decide %.2f ms\n", w.n_slots, iters, ms_i, ms_s, ms_d);
+        for (auto &e : ev) cudaEventDestroy(e);
+        cudaFreeHost(flag);
+        *launches += 3 * iters;
+        b.d_iterations = nullptr;
+        return 0;
+    }
     // the loop as a CUDA-graph WHILE node: intersect -> shade -> decide, repeated on the device until no slot is alive
     if (b.exec) {  // the previous render's graph may still be running on this stream
         R1_WF_CUDA(cudaStreamSynchronize(stream));

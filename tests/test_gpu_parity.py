@@ -31,7 +31,7 @@ def scenes(r1):
 
 # ---- hit() ----------------------------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("variant", ["mega", "scalar"])
+@pytest.mark.parametrize("variant", ["mega", "coop", "scalar"])
 @pytest.mark.parametrize("name", SCENES)
 def test_hit_matches_reference_golden(r1, scenes, golden_rays, name, variant):
     g = golden_rays[name]
@@ -234,8 +234,9 @@ def test_bitwise_invariance(r1, scenes):
     base, r0 = s.render(w, h, spp)
     again, r1_ = s.render(w, h, spp)
     assert np.array_equal(base, again) and r0.num_rays == r1_.num_rays
-    scal, rs = s.render(w, h, spp, variant=r1.VARIANT_MEGAKERNEL_SCALAR)
-    assert np.array_equal(base, scal) and rs.num_rays == r0.num_rays
+    for v in (r1.VARIANT_MEGAKERNEL_SCALAR, r1.VARIANT_MEGAKERNEL_COOP):
+        alt, ra = s.render(w, h, spp, variant=v)
+        assert np.array_equal(base, alt) and ra.num_rays == r0.num_rays, v
     more, rm = s.render(w, h, spp, blocks_per_sm=2)
     assert np.array_equal(base, more) and rm.num_rays == r0.num_rays
     for threads in (512, 768):

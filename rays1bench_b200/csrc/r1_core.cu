@@ -335,7 +335,16 @@ int r1_scene_commit(r1_scene *scene, int device)
         scan[4 * (f4 + 0) + k] = real ? -scene->cx[i] : 0.0f;
         scan[4 * (f4 + 4) + k] = real ? -scene->cy[i] : 0.0f;
         scan[4 * (f4 + 8) + k] = real ? -scene->cz[i] : 0.0f;
-        scan[4 * (f4 + 12) + k] = real ? -(scene->radius_sq[i] * (1.0f + 1.0f / 256.0f)) : inf;
+        // kk = |c|^2 - r^2 - 2^-17 |c|^2, evaluated in double and rounded DOWN (r1_device.cuh "Filter arithmetic")
+        if (real) {
+            const double c2 = (double)scene->cx[i] * scene->cx[i] + (double)scene->cy[i] * scene->cy[i] + (double)scene->cz[i] * scene->cz[i];
+            const double kk = c2 - (double)scene->radius_sq[i] - c2 / 131072.0;
+            float kf = (float)kk;
+            if ((double)kf > kk) kf = std::nextafter(kf, -inf);
+            scan[4 * (f4 + 12) + k] = std::nextafter(kf, -inf);
+        } else {
+            scan[4 * (f4 + 12) + k] = inf;
+        }
         kind[i] = R1_MAT_NONE;
         if (i < n) {
             exact[i] = make_float4(scene->cx[i], scene->cy[i], scene->cz[i], scene->radius_sq[i]);

@@ -77,6 +77,37 @@ def test_hit_matches_oracle_on_fresh_rays(r1, scenes, oracle, name):
     oracle.scene_destroy(so)
 
 
+@pytest.mark.parametrize("variant", ["mega", "coop", "scalar"])
+@pytest.mark.parametrize("name", ("large", "synth4096"))
+def test_filter_is_conservative_for_far_and_grazing_rays(r1, scenes, oracle, name, variant):
+    """The 8-instruction filter works in the expanded form (cancellation at |o|^2 + |c|^2): rays from far away that graze
+    a sphere within +-2 % of its radius are where a non-conservative filter would lose hits.  Bit-exact vs the oracle."""
+    rng = np.random.default_rng(4321)
+    soa = scenes[name].soa()
+    real = np.where(soa["inv_radius"] > 0)[0]
+    n = 6000
+    idx = rng.choice(real, n)
+    ctr = np.stack([soa["cx"][idx], soa["cy"][idx], soa["cz"][idx]], 1).astype(np.float64)
+    rad = 1.0 / soa["inv_radius"][idx].astype(np.float64)
+    u = rng.normal(size=(n, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    u[:, 1] = np.abs(u[:, 1])                                   # stay above the ground plane
+    dist = rng.choice([5.0, 50.0, 300.0, 2000.0, 20000.0], n)
+    org = ctr + u * dist[:, None]
+    side = np.cross(u, rng.normal(size=(n, 3))); side /= np.linalg.norm(side, axis=1, keepdims=True)
+    target = ctr + side * (rad * rng.uniform(0.98, 1.02, n))[:, None]
+    d = target - org; d /= np.linalg.norm(d, axis=1, keepdims=True)
+    org, d = org.astype(np.float32), d.astype(np.float32)
+    so = oracle.scene_create(name)
+    want = oracle.hit(so, org, d)
+    oracle.scene_destroy(so)
+    got = scenes[name].trace_rays(org, d, variant=r1.VARIANTS[variant])
+    assert np.array_equal(got[0], want[0]), "%d rays lost or gained a hit" % int((got[0] != want[0]).sum())
+    m = want[0] >= 0
+    assert m.sum() > 1500
+    assert np.array_equal(bits(got[1][m]), bits(want[1][m]))
+    assert np.array_equal(bits(got[3][m]), bits(want[3][m]))
+
+
 def test_hit_empty_and_single(r1, scenes):
     idx, t, p, n = scenes["small"].trace_rays(np.zeros((0, 3)), np.zeros((0, 3)))
     assert idx.shape == (0,)

@@ -37,6 +37,9 @@ WORKLOADS = {
     "synth4096": ("synth4096", 1280, 720, 250, 50) # config 5
 }
 METRIC = "Mrays/s (large scene)"
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE megakernel launch, from the ncu --set full capture summarised in
+# profiles/r01_ncu_megakernel_large.md (capture D); null for workloads that were not captured
+NCU_TRAFFIC_BYTES = {("large", "mega"): 17382656 + 877844480}
 NOMINAL_SM_MHZ = 1965.0
 
 
@@ -296,7 +299,9 @@ def main():
                                (peak_scalar, peak_packed, mhz_est),
                 "peak_nominal": peak_nominal, "frac_nominal": achieved / peak_nominal,
                 "flops_per_ray": f_ray, "flops_model": "16 per ray-sphere test (FMA=2) x %d real spheres + 70 shading (SURVEY.md 8d)" % n_real,
-                "traffic": None,
+                "traffic": NCU_TRAFFIC_BYTES.get((args.workload, args.variant)) if world == 1 else None,
+                "traffic_note": "DRAM bytes per megakernel launch (ncu); algorithmic FLOPs are the REFERENCE's 16 per test, the filter "
+                                "executes 8 FMA-pipe instructions per test plus an exact re-test of the 0.4 % candidates",
                 "hbm": {"algorithmic_bytes_per_step": hbm_bytes, "achieved_gbs": hbm_bytes * args.steps / (ms_trace * 1e-3) / 1e9,
                         "note": "partial sums written + read once, RGB8 out, sphere staging per CTA: HBM is idle on this path"}}
     try:

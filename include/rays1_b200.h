@@ -151,6 +151,11 @@ int r1_host_set_quiet(int quiet);
  * commit != 0 also uploads the device buffers to GPUs 0 .. n_gpus-1 (what the C++ builders always do); commit == 0
  * builds the host SoA only.  Returns a Scene* (see rays1_host.h) or NULL (r1_last_error() says why). */
 void *r1_host_create_scene(const char *name, int commit);
+/* Scene from a text description (scenes beyond the three hard-coded builders).  One statement per line:
+ *   camera <from.xyz> <at.xyz> <vfov_deg> <aperture> <focus_dist>
+ *   sphere <c.xyz> <radius> lambert <r> <g> <b> | metal <r> <g> <b> <fuzz> | dielectric <ior> | none
+ * Padded to a multiple of 8 like the built-in scenes.  Returns a Scene* or NULL. */
+void *r1_host_create_scene_from_file(const char *path, int commit);
 /* The r1_scene inside a host Scene (borrowed). */
 r1_scene *r1_host_scene_handle(void *scene);
 /* benchmark(scene, pixels, write_tga, scene_name) (rayweek1.cpp:845-927): renders, prints the reference's report block,

@@ -80,6 +80,7 @@ def _load():
         "r1_host_configure": (ci, [ci, ci, ci, ci, ci, ci, C.c_uint32]),
         "r1_host_set_quiet": (ci, [ci]),
         "r1_host_create_scene": (vp, [C.c_char_p, ci]),
+        "r1_host_create_scene_from_file": (vp, [C.c_char_p, ci]),
         "r1_host_scene_handle": (vp, [vp]),
         "r1_host_benchmark": (ci, [vp, u8p, ci, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
         "r1_host_destroy_scene": (None, [vp]),
@@ -220,6 +221,27 @@ def configure(width=0, height=0, spp=0, max_bounces=0, variant=-1, n_gpus=0, see
 def create_scene(name, commit=True):
     """commit=False builds the host SoA only (no GPU needed); such a scene cannot render."""
     return Scene(lib.r1_host_create_scene(name.encode(), 1 if commit else 0), name)
+
+
+def create_scene_from_file(path, commit=True):
+    """Scene from a text description (see include/rays1_b200.h: camera / sphere statements)."""
+    return Scene(lib.r1_host_create_scene_from_file(os.fsencode(path), 1 if commit else 0), os.path.basename(path))
+
+
+def write_scene_file(path, camera_args, spheres):
+    """camera_args = (from xyz, at xyz, vfov, aperture, focus); spheres = iterable of (cx, cy, cz, radius, kind, r, g, b, param)."""
+    names = {MAT_LAMBERT: "lambert", MAT_METAL: "metal", MAT_DIELECTRIC: "dielectric", MAT_NONE: "none"}
+    with open(path, "w") as f:
+        f.write("camera " + " ".join("%.9g" % v for v in camera_args) + "\n")
+        for cx, cy, cz, radius, kind, r, g, b, param in spheres:
+            f.write("sphere %.9g %.9g %.9g %.9g %s" % (cx, cy, cz, radius, names[int(kind)]))
+            if kind == MAT_LAMBERT:
+                f.write(" %.9g %.9g %.9g" % (r, g, b))
+            elif kind == MAT_METAL:
+                f.write(" %.9g %.9g %.9g %.9g" % (r, g, b, param))
+            elif kind == MAT_DIELECTRIC:
+                f.write(" %.9g" % param)
+            f.write("\n")
 
 
 def create_small_scene():

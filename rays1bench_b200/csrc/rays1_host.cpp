@@ -42,10 +42,10 @@ struct Builder {
     Scene *scene;
     bool ok = true;
     explicit Builder(uint32_t reserve) : scene(new Scene) { scene->handle = r1_scene_create(reserve); }
-    void camera(float fx, float fy, float fz, float vfov, float aperture, float focus)
+    void camera(float fx, float fy, float fz, float vfov, float aperture, float focus, float ax = 0, float ay = 0, float az = 0)
     {
         const HostConfig &cfg = host_config();
-        const float from[3] = { fx, fy, fz }, at[3] = { 0, 0, 0 }, up[3] = { 0, 1, 0 };
+        const float from[3] = { fx, fy, fz }, at[3] = { ax, ay, az }, up[3] = { 0, 1, 0 };
         // aspect = (float)SCREEN_W / (float)SCREEN_H (rayweek1.cpp:564)
         if (r1_scene_set_camera(scene->handle, from, at, up, vfov, (float)cfg.width / (float)cfg.height, aperture, focus)) ok = false;
     }
@@ -153,6 +153,46 @@ Scene *build_by_name(const char *name)
     return nullptr;
 }
 
+// Scene description files: what the reference hard-codes in create_*_scene(), as text, so that
+// sphere-count sweeps do not need a recompile.  One statement per line, '#' starts a comment:
+//   camera <from.xyz> <at.xyz> <vfov_deg> <aperture> <focus_dist>           (up is +y, aspect = width / height)
+//   sphere <c.xyz> <radius> lambert <r> <g> <b> | metal <r> <g> <b> <fuzz> | dielectric <ior> | none
+Scene *build_from_file(const char *path)
+{
+    FILE *f = fopen(path, "rt");
+    if (!f) return nullptr;
+    Builder b(64);
+    bool have_camera = false;
+    char line[512];
+    int lineno = 0;
+    while (b.ok && fgets(line, sizeof(line), f)) {
+        ++lineno;
+        if (char *hash = strchr(line, '#')) *hash = 0;
+        char word[32], mat[32];
+        float v[10];
+        if (sscanf(line, "%31s", word) != 1) continue;
+        if (!strcmp(word, "camera")) {
+            if (sscanf(line, "%*s %f %f %f %f %f %f %f %f %f", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6], &v[7], &v[8]) != 9) b.ok = false;
+            else { b.camera(v[0], v[1], v[2], v[6], v[7], v[8], v[3], v[4], v[5]); have_camera = true; }
+        } else if (!strcmp(word, "sphere")) {
+            int n = 0;
+            if (sscanf(line, "%*s %f %f %f %f %31s%n", &v[0], &v[1], &v[2], &v[3], mat, &n) != 5) { b.ok = false; break; }
+            const char *rest = line + n;
+            if (!strcmp(mat, "lambert") && sscanf(rest, "%f %f %f", &v[4], &v[5], &v[6]) == 3) b.lambert(v[0], v[1], v[2], v[3], v[4], v[5], v[6]);
+            else if (!strcmp(mat, "metal") && sscanf(rest, "%f %f %f %f", &v[4], &v[5], &v[6], &v[7]) == 4) b.metal(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+            else if (!strcmp(mat, "dielectric") && sscanf(rest, "%f", &v[4]) == 1) b.dielectric(v[0], v[1], v[2], v[3], v[4]);
+            else if (!strcmp(mat, "none")) b.add(v[0], v[1], v[2], v[3], R1_MAT_NONE, 0, 0, 0, 0);
+            else b.ok = false;
+        } else {
+            b.ok = false;
+        }
+        if (!b.ok) fprintf(stderr, "rays1_b200: %s:%d: cannot parse '%s'\n", path, lineno, word);
+    }
+    fclose(f);
+    if (!have_camera) b.ok = false;
+    return b.finish();
+}
+
 Scene *must(Scene *s, const char *name)
 {
     if (!s) die(name);
@@ -167,6 +207,7 @@ Scene *create_medium_scene() { return must(build_by_name("medium"), "create_medi
 Scene *create_large_scene() { return must(build_by_name("large"), "create_large_scene"); }
 Scene *create_synth4096_scene() { return must(build_by_name("synth4096"), "create_synth4096_scene"); }
 Scene *create_scene_by_name(const char *name) { return build_by_name(name); }
+Scene *create_scene_from_file(const char *path) { return build_from_file(path); }
 
 // ------------------------------------------------------------------------------------------------ multi-GPU
 // One process, G devices: every device renders its interleaved row tiles (r1_render_device, asynchronous), then
@@ -441,6 +482,15 @@ void *r1_host_create_scene(const char *name, int commit)
     if (!name) return nullptr;
     g_commit = commit != 0;
     Scene *s = build_by_name(name);
+    g_commit = true;
+    return s;
+}
+
+void *r1_host_create_scene_from_file(const char *path, int commit)
+{
+    if (!path) return nullptr;
+    g_commit = commit != 0;
+    Scene *s = build_from_file(path);
     g_commit = true;
     return s;
 }

@@ -48,6 +48,7 @@ Scene *create_medium_scene();
 Scene *create_large_scene();
 Scene *create_synth4096_scene();  // SURVEY.md 8d config 5; not in the reference
 Scene *create_scene_by_name(const char *name);
+Scene *create_scene_from_file(const char *path);  // text scene description (rays1_host.cpp); nullptr on error
 
 RESULT benchmark(Scene *scene, Pix *pixels, bool write_tga, const char *scene_name);
 void log_results(const char *version, const char *scene, const RESULT *results, int num_runs);

@@ -2,6 +2,7 @@
 // prints the reference's report blocks and writes out_<scene>.txt (and out_<scene>.tga with -w), exactly as
 // src/latest/rayweek1.cpp:930-988 does.  Extra flags (not in the reference) select what it fixes at compile time:
 //   --gpus N  --variant mega|wavefront|scalar|coop  --width W --height H --spp S --bounces B  --scene NAME (repeatable)
+//   --scene-file PATH (text scene description, see rays1_host.cpp)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -33,6 +34,7 @@ int main(int argc, const char *argv[])
         else if (strcmp(argv[i], "--bounces") == 0) cfg.max_bounces = next_int(0);
         else if (strcmp(argv[i], "--seed") == 0) cfg.seed = (uint32_t)next_int(0);
         else if (strcmp(argv[i], "--scene") == 0 && i + 1 < argc) scenes.push_back(argv[++i]);
+        else if (strcmp(argv[i], "--scene-file") == 0 && i + 1 < argc) scenes.push_back(std::string("@") + argv[++i]);
         else if (strcmp(argv[i], "--variant") == 0 && i + 1 < argc) {
             const char *v = argv[++i];
             if (!strcmp(v, "mega")) cfg.variant = R1_VARIANT_MEGAKERNEL;
@@ -50,11 +52,17 @@ int main(int argc, const char *argv[])
     const char *version = "b200";
     for (const std::string &name : scenes) {
         for (int i = 0; i < num_runs; ++i) {
-            Scene *scene = create_scene_by_name(name.c_str());
+            // "@path" = a scene description file; it is reported under the file's base name
+            Scene *scene = name[0] == '@' ? create_scene_from_file(name.c_str() + 1) : create_scene_by_name(name.c_str());
             if (!scene) { printf("Unknown scene: %s\n", name.c_str()); return 2; }
-            results[i] = benchmark(scene, pixels, write_tga, name.c_str());
+            std::string label = name;
+            if (name[0] == '@') {
+                label = name.substr(name.find_last_of('/') == std::string::npos ? 1 : name.find_last_of('/') + 1);
+                label = label.substr(0, label.find('.'));
+            }
+            results[i] = benchmark(scene, pixels, write_tga, label.c_str());
+            if (i == num_runs - 1) log_results(version, label.c_str(), results, num_runs);
         }
-        log_results(version, name.c_str(), results, num_runs);
     }
     delete[] pixels;
     return 0;

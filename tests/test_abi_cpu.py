@@ -206,3 +206,49 @@ def test_two_collective_exchange_world2_gloo(tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "GLOO_OK" in out.stdout
+
+
+def test_scene_file_round_trip_matches_builtin_builders(r1, tmp_path):
+    """the text scene format reproduces create_large_scene() / the 4096-sphere scene bit for bit."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_scene
+    for name, args in (("large", (30, 16, 0, (3, 8, 15), 10.0)), ("synth4096", (66, 62, 480, (6, 16, 30), 20.0))):
+        cam, sph = make_scene.grid_scene(*args)
+        path = str(tmp_path / (name + ".r1scene"))
+        r1.write_scene_file(path, cam, sph)
+        a = r1.create_scene_from_file(path, commit=False)
+        b = r1.create_scene(name, commit=False)
+        sa, sb = a.soa(), b.soa()
+        assert a.count() == b.count()
+        for k in sa:
+            assert np.array_equal(sa[k].view(np.uint32) if sa[k].dtype == np.float32 else sa[k],
+                                  sb[k].view(np.uint32) if sb[k].dtype == np.float32 else sb[k]), (name, k)
+        assert np.array_equal(a.camera(), b.camera())
+        a.close()
+        b.close()
+    bad = tmp_path / "bad.r1scene"
+    bad.write_text("camera 0 0 5 0 0 0 60 0.1 5\nsphere 0 0 0 1 plastic 1 1 1\n")
+    with pytest.raises(r1.Rays1Error):
+        r1.create_scene_from_file(str(bad), commit=False)
+    with pytest.raises(r1.Rays1Error):
+        r1.create_scene_from_file(str(tmp_path / "missing.r1scene"), commit=False)
+
+
+def test_compare_tga_tool(r1, tmp_path):
+    """TGA reader / RMSE / PNG export agree with the writer (BGR, bottom-up)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import compare_tga
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (9, 16, 3), dtype=np.uint8)      # row 0 = bottom, RGB
+    px = img.copy()
+    r1.tga_write_rgb24(str(tmp_path / "a.tga"), 16, 9, px)
+    got = compare_tga.read_image(str(tmp_path / "a.tga"))
+    assert np.array_equal(got, img[::-1])                        # top-down RGB
+    other = img.copy()
+    other[0, 0, 0] ^= 0x10
+    np.savez(tmp_path / "b.npz", rgb=other)
+    r = compare_tga.compare(got, compare_tga.read_image(str(tmp_path / "b.npz")))
+    assert r["max_abs"] == 16 and not r["identical"] and 0 < r["rmse"] < 1
+    compare_tga.write_png(str(tmp_path / "a.png"), got)
+    raw = open(tmp_path / "a.png", "rb").read()
+    assert raw[:8] == b"\x89PNG\r\n\x1a\n" and b"IDAT" in raw

@@ -363,3 +363,24 @@ def test_in_process_multi_gpu_matches_single_gpu(r1, tmp_path):
         rays = [l for l in out.stdout.splitlines() if l.startswith("total rays:")][0]
         outs[g] = (open(d / "out_large.tga", "rb").read(), rays)
     assert outs[1] == outs[2]
+
+
+def test_scene_file_renders_like_builtin_scene(r1, tmp_path):
+    """--scene-file through the executable: same bytes as the built-in large scene."""
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_scene
+    cam, sph = make_scene.grid_scene(30, 16, 0, (3, 8, 15), 10.0)
+    path = str(tmp_path / "large.r1scene")
+    r1.write_scene_file(path, cam, sph)
+    common = ["-w", "--spp", "8", "--width", "320", "--height", "180"]
+    a = subprocess.run([r1.EXE_PATH, "--scene-file", path] + common, cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert a.returncode == 0, a.stderr
+    file_tga = open(tmp_path / "out_large.tga", "rb").read()
+    file_txt = open(tmp_path / "out_large.txt").read()
+    os.remove(tmp_path / "out_large.tga")
+    b = subprocess.run([r1.EXE_PATH, "--scene", "large"] + common, cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert b.returncode == 0, b.stderr
+    assert open(tmp_path / "out_large.tga", "rb").read() == file_tga
+    assert file_txt.split("|")[2] == open(tmp_path / "out_large.txt").read().split("|")[2]   # same ray count

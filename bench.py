@@ -41,6 +41,9 @@ METRIC = "Mrays/s (large scene)"
 # profiles/r01_ncu_megakernel_large.md (capture D); null for workloads that were not captured
 NCU_TRAFFIC_BYTES = {("large", "mega"): 17382656 + 877844480}
 NOMINAL_SM_MHZ = 1965.0
+# the reference's own published figure for this metric and configuration (step13, large scene,
+# 1280x720, 250 spp) -- 59.362 Mrays/s on an i9-9900K 8c/16t, README.md:52 of the reference.  CPU hardware, quoted as published.
+PUBLISHED_MRAYS = {"large": 59.362, "medium": 215.403, "small": 321.238}
 
 
 def workload_label(name):
@@ -152,7 +155,8 @@ def main():
         steps, warmup = args.steps, max(args.warmup, 1)
         r = cpu_reference(args.workload, args.cpu_budget, steps, warmup)
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "Mrays/s", "n_gpus": args.gpus, "steps": steps,
-                "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": r["value"] / PUBLISHED_MRAYS[args.workload] if args.workload in PUBLISHED_MRAYS else None,
                 "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": r["value"], "unit": "Mrays/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -311,7 +315,9 @@ def main():
         pass
 
     line = {"metric": METRIC, "value": total_rays / (ms_value * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": (total_rays / (ms_value * 1e-3) / 1e6) / PUBLISHED_MRAYS[args.workload] if args.workload in PUBLISHED_MRAYS else None,
+            "baseline_note": "published by the reference for this scene at 1280x720x250 on an i9-9900K (BASELINE.md section 1); no GPU number is published",
             "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / args.steps,

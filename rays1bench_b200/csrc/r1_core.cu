@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
@@ -448,9 +449,11 @@ int r1_render_device(r1_scene *scene, const r1_render_params *params, void *d_rg
         if (rc) return rc;
         a.partial = x.partial;
         R1_CUDA(cudaMemsetAsync(x.unit_counter, 0, sizeof(unsigned int), stream));
-        const bool staged = c.dev.n_pad <= r1::kMaxStagedSpheres;
+        // scenes of up to 4096 spheres are staged in shared memory; R1_FORCE_UNSTAGED=1 exercises the global-memory path on small scenes
+        const bool staged = c.dev.n_pad <= r1::kMaxStagedSpheres && !getenv("R1_FORCE_UNSTAGED");
         R1_CUDA(cudaEventRecord(x.ev[1], stream));
         if (prm.variant == R1_VARIANT_WAVEFRONT) {
+            if (c.dev.n_pad > r1::kMaxStagedSpheres) return fail(R1_ERR_LIMIT, "the wavefront variant stages at most %d spheres", r1::kMaxStagedSpheres);
             uint32_t launches = 0;
             rc = r1::wavefront_render(x.wf, a, x.sm_count, stream, &launches);
             if (rc) return fail(R1_ERR_CUDA, "wavefront: %s", cudaGetErrorString((cudaError_t)rc));

@@ -384,3 +384,36 @@ def test_scene_file_renders_like_builtin_scene(r1, tmp_path):
     assert b.returncode == 0, b.stderr
     assert open(tmp_path / "out_large.tga", "rb").read() == file_tga
     assert file_txt.split("|")[2] == open(tmp_path / "out_large.txt").read().split("|")[2]   # same ray count
+
+
+def test_unstaged_global_memory_scan_matches_staged(r1, scenes, monkeypatch):
+    """scenes above 4096 spheres scan from global memory instead of shared memory (template flag kStaged); forced here on
+    the large scene so that the two paths can be compared byte for byte"""
+    s = scenes["large"]
+    base, r0 = s.render(160, 90, 24)
+    monkeypatch.setenv("R1_FORCE_UNSTAGED", "1")
+    for v in (r1.VARIANT_MEGAKERNEL, r1.VARIANT_MEGAKERNEL_COOP, r1.VARIANT_MEGAKERNEL_SCALAR):
+        alt, ra = s.render(160, 90, 24, variant=v)
+        assert np.array_equal(base, alt) and ra.num_rays == r0.num_rays, v
+
+
+def test_scene_above_staging_limit(r1, tmp_path):
+    """5044 spheres (> 4096): the megakernel renders from global memory; the staged-only entry points say so"""
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_scene
+    cam, sph = make_scene.grid_scene(72, 70, 480, (7, 18, 34), 22.0)
+    path = str(tmp_path / "big.r1scene")
+    r1.write_scene_file(path, cam, sph)
+    s = r1.create_scene_from_file(path)
+    assert s.count() == 5048
+    rgb, res = s.render(96, 54, 16)
+    assert rgb.any() and 96 * 54 * 16 < res.num_rays < 96 * 54 * 16 * 6
+    again, _ = s.render(96, 54, 16, world=2, rank=0)
+    assert np.array_equal(again, rgb[[r1.global_row(lr, 8, 0, 2) for lr in range(again.shape[0])]])
+    with pytest.raises(r1.Rays1Error, match="stages at most"):
+        s.render(96, 54, 16, variant=r1.VARIANT_WAVEFRONT)
+    with pytest.raises(r1.Rays1Error, match="stages at most"):
+        s.trace_rays([[0, 5, 20]], [[0, 0, -1]])
+    s.close()

@@ -145,7 +145,7 @@ def main():
         raise SystemExit("--gpus %d does not match WORLD_SIZE %d" % (args.gpus, world))
     scene_name, W, H, SPP, MB = WORKLOADS[args.workload]
     config = {"workload": workload_label(args.workload), "scene": scene_name, "width": W, "height": H, "spp": SPP, "max_bounces": MB,
-              "partition": "interleaved row tiles of 8 rows, tile k -> rank k %% %d" % world, "variant": args.variant,
+              "partition": "interleaved row tiles of 1 row, row k -> rank k %% %d" % world, "variant": args.variant,
               "l2": "flushed between timed steps (256 MiB write); the kernel's inputs (<= 128 KB of spheres) are staged to shared memory"}
 
     # -------------------------------------------------------------------------------------------- reference arm
@@ -179,7 +179,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     variant = r1.VARIANTS[args.variant]
-    row_tile = 8
+    row_tile = r1.DEFAULT_ROW_TILE
     r1.configure(width=W, height=H, spp=SPP, max_bounces=MB, variant=variant, n_gpus=1, seed=0, quiet=True)
 
     def barrier():

@@ -63,7 +63,7 @@ typedef struct r1_render_params {
     int32_t variant;         /* R1_VARIANT_* */
     uint32_t seed;           /* global seed of the counter-based RNG */
     int32_t rank, world;     /* this call renders the row tiles k with k % world == rank (world = 1: all rows) */
-    int32_t row_tile;        /* rows per interleaved tile; <= 0 -> 8 */
+    int32_t row_tile;        /* rows per interleaved tile; <= 0 -> 1 (single rows balance the ranks best) */
     int32_t blocks_per_sm;   /* persistent CTAs per SM; <= 0 -> tuned default */
     int32_t threads;         /* threads per CTA: 512, 768 or 1024; <= 0 -> tuned default */
     int32_t device;          /* CUDA device to run on (must have been committed); < 0 -> device of the last commit */

@@ -21,6 +21,7 @@ MAT_NONE, MAT_LAMBERT, MAT_METAL, MAT_DIELECTRIC = -1, 0, 1, 2
 
 # the reference's compile-time workload (src/common/common.h:18-25)
 SCREEN_W, SCREEN_H, NUM_SAMPLES_PER_PIXEL, MAX_BOUNCES = 1280, 720, 250, 50
+DEFAULT_ROW_TILE = 1  # rows per interleaved tile of the multi-GPU partition (library default)
 
 
 class Rays1Error(RuntimeError):
@@ -155,7 +156,7 @@ class Scene:
 
     # -- device entry points
     def render(self, width=SCREEN_W, height=SCREEN_H, spp=NUM_SAMPLES_PER_PIXEL, max_bounces=MAX_BOUNCES, variant=VARIANT_MEGAKERNEL,
-               seed=0, rank=0, world=1, row_tile=8, device=-1, blocks_per_sm=0, threads=0):
+               seed=0, rank=0, world=1, row_tile=DEFAULT_ROW_TILE, device=-1, blocks_per_sm=0, threads=0):
         """r1_render: host buffer out.  Returns (rgb[local_rows, width, 3] uint8 with row 0 = bottom, Result)."""
         p = RenderParams(width, height, spp, max_bounces, variant, seed, rank, world, row_tile, blocks_per_sm, threads, device)
         rows = int(lib.r1_local_rows(height, row_tile, rank, world))
@@ -169,7 +170,7 @@ class Scene:
         """r1_render_device: asynchronous, device pointers (e.g. torch tensors' data_ptr())."""
         p = RenderParams(kw.get("width", SCREEN_W), kw.get("height", SCREEN_H), kw.get("spp", NUM_SAMPLES_PER_PIXEL),
                          kw.get("max_bounces", MAX_BOUNCES), kw.get("variant", VARIANT_MEGAKERNEL), kw.get("seed", 0), kw.get("rank", 0),
-                         kw.get("world", 1), kw.get("row_tile", 8), kw.get("blocks_per_sm", 0), kw.get("threads", 0), kw.get("device", -1))
+                         kw.get("world", 1), kw.get("row_tile", DEFAULT_ROW_TILE), kw.get("blocks_per_sm", 0), kw.get("threads", 0), kw.get("device", -1))
         res = Result()
         _check(lib.r1_render_device(self.handle, C.byref(p), C.c_void_p(d_rgb_ptr), C.c_void_p(d_num_rays_ptr),
                                     C.c_void_p(stream_ptr or 0), C.byref(res)), "r1_render_device")
@@ -315,7 +316,7 @@ def global_row(local_row, row_tile, rank, world):
     return int(lib.r1_global_row(local_row, row_tile, rank, world))
 
 
-def assemble_rows(parts, height, row_tile=8):
+def assemble_rows(parts, height, row_tile=DEFAULT_ROW_TILE):
     """Host-side de-interleave of per-rank row blocks (used by tests; the product path does this on the GPU)."""
     world = len(parts)
     width = parts[0].shape[1]

@@ -17,7 +17,7 @@ struct HostConfig {
     int variant = R1_VARIANT_MEGAKERNEL;
     int n_gpus = 1;
     uint32_t seed = 0;
-    int row_tile = 8;
+    int row_tile = 1;                // rows per interleaved tile of the multi-GPU partition
     bool quiet = false;              // suppress the stdout report (used by ctypes callers that print their own)
 };
 HostConfig &host_config();

@@ -241,7 +241,7 @@ def test_wavefront_full_size_matches_megakernel(r1, scenes, name):
     b, rb = scenes[name].render(1280, 720, 32, variant=r1.VARIANT_WAVEFRONT)
     assert np.array_equal(a, b) and ra.num_rays == rb.num_rays
     part, rp = scenes[name].render(1280, 720, 32, variant=r1.VARIANT_WAVEFRONT, rank=1, world=4)
-    rows = [r1.global_row(lr, 8, 1, 4) for lr in range(part.shape[0])]
+    rows = [r1.global_row(lr, r1.DEFAULT_ROW_TILE, 1, 4) for lr in range(part.shape[0])]
     assert np.array_equal(part, a[rows])
 
 
@@ -284,6 +284,8 @@ def test_bitwise_invariance(r1, scenes):
             rays += res.num_rays
         assert np.array_equal(r1.assemble_rows(parts, h), base), world
         assert rays == r0.num_rays
+    parts = [s.render(w, h, spp, rank=rank, world=3, row_tile=8)[0] for rank in range(3)]   # 8-row tiles give the same picture
+    assert np.array_equal(r1.assemble_rows(parts, h, 8), base)
     other, _ = s.render(w, h, spp, seed=1)
     assert not np.array_equal(base, other)
     assert rmse(base, other) < 12
@@ -300,7 +302,7 @@ def test_edge_sizes_and_depth_cap(r1, scenes):
     rgb1, res1 = s.render(64, 36, 16, max_bounces=1)
     rgb50, res50 = s.render(64, 36, 16, max_bounces=50)
     assert res1.num_rays < res50.num_rays <= 64 * 36 * 16 * 51
-    rgb, res = s.render(40, 10, 2, rank=7, world=8)    # a rank that owns no rows
+    rgb, res = s.render(40, 10, 2, rank=7, world=8, row_tile=8)    # a rank that owns no rows
     assert rgb.shape[0] == 0 and res.num_rays == 0
     rgb, res = s.render(640, 360, 1)
     assert res.num_samples == 640 * 360
@@ -411,7 +413,7 @@ def test_scene_above_staging_limit(r1, tmp_path):
     rgb, res = s.render(96, 54, 16)
     assert rgb.any() and 96 * 54 * 16 < res.num_rays < 96 * 54 * 16 * 6
     again, _ = s.render(96, 54, 16, world=2, rank=0)
-    assert np.array_equal(again, rgb[[r1.global_row(lr, 8, 0, 2) for lr in range(again.shape[0])]])
+    assert np.array_equal(again, rgb[[r1.global_row(lr, r1.DEFAULT_ROW_TILE, 0, 2) for lr in range(again.shape[0])]])
     with pytest.raises(r1.Rays1Error, match="stages at most"):
         s.render(96, 54, 16, variant=r1.VARIANT_WAVEFRONT)
     with pytest.raises(r1.Rays1Error, match="stages at most"):

@@ -39,7 +39,8 @@ WORKLOADS = {
 METRIC = "Mrays/s (large scene)"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE megakernel launch, from the ncu --set full capture summarised in
 # profiles/r01_ncu_megakernel_large.md (capture D); null for workloads that were not captured
-NCU_TRAFFIC_BYTES = {("large", "mega"): 17382656 + 877844480}
+NCU_TRAFFIC_BYTES = {("large", "mega"): 17382656 + 877844480}  # capture D: the build with float partial sums (58 M x 16 B);
+#                                                                    the fixed-point accumulators since then are 32 B per pixel
 NOMINAL_SM_MHZ = 1965.0
 # the reference's own published figure for this metric and configuration (step13, large scene,
 # 1280x720, 250 spp) -- 59.362 Mrays/s on an i9-9900K 8c/16t, README.md:52 of the reference.  CPU hardware, quoted as published.
@@ -294,9 +295,7 @@ def main():
     sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
     peak_nominal = sm_count * 128 * 2 * NOMINAL_SM_MHZ * 1e6 / 1e12
     achieved = total_rays * f_ray / (ms_trace * 1e-3) / 1e12 / world  # per GPU
-    spu = max(4, (SPP + 63) // 64)
-    n_chunks = (SPP + spu - 1) // spu
-    hbm_bytes = W * H * (n_chunks * 16 * 2 + 3) + n_pad * 32 * sm_count
+    hbm_bytes = W * H * (32 * 2 + 3) + n_pad * 32 * sm_count   # fixed-point accumulators zeroed + written back, RGB8 out, staging
     roofline = {"bound": "fp32_fma", "kernel": "r1::megakernel" if args.variant != "wavefront" else "r1::wf_intersect + wf_shade (graph loop)", "achieved": achieved,
                 "peak": peak_meas, "unit": "TFLOP/s", "frac": achieved / peak_meas,
                 "peak_source": "FFMA/FFMA2 chain microbenchmark on this GPU (r1_fma_peak), per GPU; scalar %.1f / packed %.1f TFLOP/s at ~%.0f MHz" %
@@ -307,7 +306,7 @@ def main():
                 "traffic_note": "DRAM bytes per megakernel launch (ncu); algorithmic FLOPs are the REFERENCE's 16 per test, the filter "
                                 "executes 8 FMA-pipe instructions per test plus an exact re-test of the 0.4 % candidates",
                 "hbm": {"algorithmic_bytes_per_step": hbm_bytes, "achieved_gbs": hbm_bytes * args.steps / (ms_trace * 1e-3) / 1e9,
-                        "note": "partial sums written + read once, RGB8 out, sphere staging per CTA: HBM is idle on this path"}}
+                        "note": "pixel accumulators (32 B, L2 atomics) + RGB8 out + sphere staging per CTA: HBM is idle on this path"}}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         roofline["hbm"]["peak_gbs"] = peaks.get("hbm_gbs")

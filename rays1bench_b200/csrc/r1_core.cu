@@ -46,13 +46,13 @@ struct DeviceCtx {
     r1::DevScene dev;
 };
 
-// Per-device scratch shared by every scene of the process (work-unit partial sums, counters, staging, events).
+// Per-device scratch shared by every scene of the process (pixel accumulators, counters, staging, events).
 // It outlives scenes so that a render does not pay cudaMalloc/cudaFree; renders on one device are serialised by the
 // caller, as the reference's benchmark() calls are (rayweek1.cpp:969-984).
 struct Scratch {
     bool ready = false;
     int sm_count = 0, cc_major = 0, cc_minor = 0;
-    float4 *partial = nullptr; size_t partial_cap = 0;
+    unsigned long long *accum = nullptr; size_t accum_cap = 0;   // npix_local x 4 fixed-point sums
     unsigned int *unit_counter = nullptr;
     uint8_t *rgb = nullptr; size_t rgb_cap = 0;
     unsigned long long *num_rays = nullptr;
@@ -140,9 +140,9 @@ int get_ctx(r1_scene *scene, DeviceCtx **out, int device = -1)
 // ray counts 4.5 % apart (max / mean), single rows 0.08 %.
 constexpr int kDefaultRowTile = 1;
 
-// samples per unit: a function of spp ONLY (see RenderArgs) -- at most 64 chunks per pixel, at least 4 samples each.
-// Small units keep the tail short: a lane needs ~0.08 ms per sample on the large scene, and a render on 8 GPUs lasts 16 ms.
-int samples_per_unit(int spp) { return std::max(4, (spp + 63) / 64); }
+// One sample per unit up to 256 spp (more only to keep the unit count below 2^32 on huge renders): the accumulators are
+// order-free, so the unit size affects scheduling granularity only, never the image.
+int samples_per_unit(int spp) { return std::max(1, (spp + 255) / 256); }
 
 struct Partition { int local_rows; uint32_t npix_local; };
 
@@ -436,7 +436,7 @@ int r1_render_device(r1_scene *scene, const r1_render_params *params, void *d_rg
     a.seed = r1::Rng::seed_hash(prm.seed);
     a.inv_w = 1.0f / prm.width; a.inv_h = 1.0f / prm.height;  // rayweek1.cpp:746
     a.inv_spp = (float)(1.0f / prm.spp);                       // rayweek1.cpp:765
-    a.magic_npix = r1::div_magic(a.npix_local);
+    a.magic_chunks = r1::div_magic((uint32_t)a.n_chunks);
     a.magic_width = r1::div_magic((uint32_t)prm.width);
     a.rgb = (uint8_t *)d_rgb;
     a.num_rays = (unsigned long long *)d_num_rays;
@@ -449,9 +449,10 @@ int r1_render_device(r1_scene *scene, const r1_render_params *params, void *d_rg
     R1_CUDA(cudaMemsetAsync(d_num_rays, 0, sizeof(unsigned long long), stream));
     R1_CUDA(cudaEventRecord(x.ev[0], stream));
     if (a.npix_local > 0) {
-        rc = grow(x.partial, x.partial_cap, (size_t)a.n_units);
+        rc = grow(x.accum, x.accum_cap, (size_t)a.npix_local * 4);
         if (rc) return rc;
-        a.partial = x.partial;
+        a.accum = x.accum;
+        R1_CUDA(cudaMemsetAsync(x.accum, 0, (size_t)a.npix_local * 4 * sizeof(unsigned long long), stream));
         R1_CUDA(cudaMemsetAsync(x.unit_counter, 0, sizeof(unsigned int), stream));
         // scenes of up to 4096 spheres are staged in shared memory; R1_FORCE_UNSTAGED=1 exercises the global-memory path on small scenes
         const bool staged = c.dev.n_pad <= r1::kMaxStagedSpheres && !getenv("R1_FORCE_UNSTAGED");

@@ -8,13 +8,17 @@ namespace r1 {
 
 constexpr unsigned kFull = 0xffffffffu;
 
-// Work decomposition: unit u = (sample chunk c, local pixel lp), u = c * npix_local + lp.  A unit is `samples_per_unit`
-// consecutive samples of one pixel, summed in order by one lane and written to partial[u]; resolve() adds a pixel's
-// chunks in ascending c.  samples_per_unit depends on spp only, so the float summation tree -- and therefore the RGB8
-// image -- is identical for every GPU count, block shape and kernel variant.
+// Work decomposition: unit u = (local pixel lp, sample chunk c), u = lp * n_chunks + c: `samples_per_unit` consecutive
+// samples of one pixel (1 sample for spp <= 256).  Lanes take RANGES of consecutive units from one global counter --
+// 16 units at a time while there is plenty of work, down to 1 near the end, so the last lanes finish within one sample of
+// each other -- and add every finished sample to the pixel's accumulator in 64-bit FIXED POINT (2^-40) with a
+// fire-and-forget atomic (RED.ADD.64).  Integer addition is associative: the sums, and therefore the RGB8 image, are
+// bit-identical for every GPU count, CTA shape, unit size and kernel variant, whatever order the samples arrive in.
+// (The reference sums floats sequentially per pixel, rayweek1.cpp:757-765; radiance per sample is in [0, 1], so 40
+// fractional bits lose < 1e-12 per sample and 2^20 samples fit.)
 struct RenderArgs {
     DevScene scene;
-    float4 *partial;                 // n_units
+    unsigned long long *accum;       // npix_local x 4 (r, g, b, -): sum of per-sample radiance * 2^40
     unsigned long long *num_rays;    // += one per traced ray (rayweek1.cpp:517)
     unsigned int *unit_counter;      // next unit to hand out
     uint8_t *rgb;                    // npix_local * 3, local rows packed, row 0 = bottom
@@ -24,8 +28,11 @@ struct RenderArgs {
     int32_t samples_per_unit, n_chunks;
     uint32_t seed;                   // Rng::seed_hash(global seed)
     float inv_w, inv_h, inv_spp;
-    uint64_t magic_npix, magic_width;  // floor(2^64 / d) + 1: exact n / d for 32-bit n via one 64-bit mul-high (0 when d == 1)
+    uint64_t magic_chunks, magic_width;  // floor(2^64 / d) + 1: exact n / d for 32-bit n via one 64-bit mul-high (0 when d == 1)
 };
+
+constexpr float kFixedScale = 1099511627776.0f;            // 2^40
+constexpr float kFixedInvScale = 9.094947017729282e-13f;   // 2^-40
 
 // n / d for n, d < 2^32 with the precomputed magic (d == 1 -> magic 0)
 __device__ __forceinline__ uint32_t fast_div(uint32_t n, uint64_t magic) { return magic ? (uint32_t)__umul64hi((uint64_t)n, magic) : n; }
@@ -68,16 +75,27 @@ __device__ __host__ __forceinline__ int global_row(int lr, int row_tile, int ran
 // The three steps of the per-path state machine, shared by the megakernel and the wavefront kernels so that both
 // execute the same instructions on the same values (bit-identical images).
 
-// unit -> (pixel, first sample, end sample)
-__device__ __forceinline__ void unit_begin(const RenderArgs &a, uint32_t unit, uint32_t &pixel, float &fx, float &fy, int &s, int &s_end)
+// unit -> (local pixel, global pixel, first sample, end sample)
+__device__ __forceinline__ void unit_begin(const RenderArgs &a, uint32_t unit, uint32_t &lp, uint32_t &pixel, float &fx, float &fy, int &s, int &s_end)
 {
-    const uint32_t c = fast_div(unit, a.magic_npix), lp = unit - c * a.npix_local;
+    lp = fast_div(unit, a.magic_chunks);
+    const uint32_t c = unit - lp * (uint32_t)a.n_chunks;
     const int lr = (int)fast_div(lp, a.magic_width), x = (int)(lp - (uint32_t)lr * (uint32_t)a.width);
     const int y = global_row(lr, a.row_tile, a.rank, a.world);
     pixel = (uint32_t)y * (uint32_t)a.width + (uint32_t)x;
     fx = (float)x; fy = (float)y;
     s = (int)c * a.samples_per_unit;
     s_end = min(s + a.samples_per_unit, a.spp);
+}
+
+// one finished sample -> the pixel's fixed-point accumulator (order-free, see RenderArgs)
+__device__ __forceinline__ void accumulate_sample(const RenderArgs &a, uint32_t lp, f3 c)
+{
+    unsigned long long *dst = a.accum + (size_t)lp * 4;
+    // fmaxf(NaN, 0) = 0: a degenerate path (zero-length scatter direction) adds nothing instead of poisoning the sum
+    atomicAdd(dst + 0, __float2ull_rn(fminf(fmaxf(c.x, 0.0f), 4.0f) * kFixedScale));
+    atomicAdd(dst + 1, __float2ull_rn(fminf(fmaxf(c.y, 0.0f), 4.0f) * kFixedScale));
+    atomicAdd(dst + 2, __float2ull_rn(fminf(fmaxf(c.z, 0.0f), 4.0f) * kFixedScale));
 }
 
 // start sample s of a pixel: jitter (rayweek1.cpp:759), lens disk + camera ray (:760, :381-386)
@@ -141,28 +159,36 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel(const __gri
     WarpScratch *ws = reinterpret_cast<WarpScratch *>(smem_raw + 16 + (kStaged ? (size_t)n_pad * 32 : 0)) + (threadIdx.x >> 5);
 
     bool active = false, exhausted = false, need_primary = false;
-    uint32_t unit = 0, pixel = 0, nrays = 0;
+    uint32_t unit = 0, unit_end = 0, lp = 0, pixel = 0, nrays = 0, last_base = 0;
     int s = 0, s_end = 0, depth = 0;
     float fx = 0.0f, fy = 0.0f;
-    f3 acc = mk3(0, 0, 0), thr = mk3(1, 1, 1);
+    f3 thr = mk3(1, 1, 1);
     f3 o = mk3(0.0f, 1.0e18f, 0.0f), d = mk3(0.0f, 0.0f, 0.0f);  // idle lanes scan a ray that passes no filter
     Rng rng;
     rng.key = 0; rng.ctr = 0;
+    const uint32_t lanes_x4 = gridDim.x * blockDim.x * 4u;
 
     for (;;) {
-        // -- take a unit (warp-aggregated: one atomic per warp per refill round)
+        // -- take a range of units (warp-aggregated: one atomic per warp per refill round).  Guided self-scheduling:
+        //    16 units per lane while more than 64 per lane remain, shrinking to 1 at the end.
         const bool want = !active && !exhausted;
         const unsigned need = __ballot_sync(kFull, want);
         if (need) {
             const int leader = __ffs(need) - 1;
-            unsigned base = 0;
-            if ((int)lane == leader) base = atomicAdd(a.unit_counter, (unsigned)__popc(need));
+            unsigned base = 0, k = 0;
+            if ((int)lane == leader) {
+                const uint32_t left = a.n_units > last_base ? a.n_units - last_base : 0u;
+                k = min(16u, max(1u, left / lanes_x4));
+                base = atomicAdd(a.unit_counter, k * (unsigned)__popc(need));
+            }
             base = __shfl_sync(kFull, base, leader);
+            k = __shfl_sync(kFull, k, leader);
+            last_base = base;
             if (want) {
-                unit = base + __popc(need & ((1u << lane) - 1u));
+                unit = base + k * __popc(need & ((1u << lane) - 1u));
+                unit_end = min(unit + k, a.n_units);
                 if (unit < a.n_units) {
-                    unit_begin(a, unit, pixel, fx, fy, s, s_end);
-                    acc = mk3(0, 0, 0);
+                    unit_begin(a, unit, lp, pixel, fx, fy, s, s_end);
                     active = true; need_primary = true;
                 } else {
                     exhausted = true;
@@ -192,13 +218,17 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel(const __gri
             f3 contrib;
             const float4 e = hit >= 0 ? s_exact[hit] : make_float4(0, 0, 0, 0);
             if (shade_step(a, hit, t, e, o, d, thr, depth, rng, contrib)) {
-                acc = add3(acc, contrib);
-                if (++s == s_end) {
-                    a.partial[unit] = make_float4(acc.x, acc.y, acc.z, 0.0f);
-                    active = false;
-                    o = mk3(0.0f, 1.0e18f, 0.0f); d = mk3(0.0f, 0.0f, 0.0f);
-                } else {
-                    need_primary = true;
+                accumulate_sample(a, lp, contrib);
+                need_primary = true;
+                if (++s == s_end) {                          // unit done: the next one of my range, or a new range
+                    if (++unit == unit_end) {
+                        active = false;
+                        o = mk3(0.0f, 1.0e18f, 0.0f); d = mk3(0.0f, 0.0f, 0.0f);
+                    } else if (s == a.spp) {
+                        unit_begin(a, unit, lp, pixel, fx, fy, s, s_end);   // first chunk of the next pixel
+                    } else {
+                        s_end = min(s + a.samples_per_unit, a.spp);        // next chunk of the same pixel
+                    }
                 }
             }
         }
@@ -212,21 +242,19 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel(const __gri
 
 // ------------------------------------------------------------------------------------------------ resolve
 // rayweek1.cpp:765-775: average, gamma 2 (sqrtf), quantise (int)(c * 255.99f) -> RGB8.
-__device__ __forceinline__ uint8_t quantise(float sum, float inv_spp)
+__device__ __forceinline__ uint8_t quantise(unsigned long long sum, float inv_spp)
 {
-    const float c = __fsqrt_rn(fmul(sum, inv_spp));
-    return (uint8_t)(int)fmul(c, 255.99f);
+    const float mean = fmul(fmul(__ull2float_rn(sum), kFixedInvScale), inv_spp);   // col *= 1 / spp  (:765)
+    const float c = __fsqrt_rn(mean);                                              // :767
+    return (uint8_t)(int)fmul(c, 255.99f);                                         // :769-775
 }
 __global__ void __launch_bounds__(256) resolve(const __grid_constant__ RenderArgs a)
 {
     for (uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x; lp < a.npix_local; lp += gridDim.x * blockDim.x) {
-        float r = 0.0f, g = 0.0f, b = 0.0f;
-        for (int c = 0; c < a.n_chunks; ++c) {
-            const float4 v = a.partial[(size_t)c * a.npix_local + lp];
-            r = fadd(r, v.x); g = fadd(g, v.y); b = fadd(b, v.z);
-        }
+        const ulonglong2 rg = *reinterpret_cast<const ulonglong2 *>(a.accum + (size_t)lp * 4);
+        const unsigned long long b = a.accum[(size_t)lp * 4 + 2];
         uint8_t *out = a.rgb + (size_t)lp * 3;
-        out[0] = quantise(r, a.inv_spp); out[1] = quantise(g, a.inv_spp); out[2] = quantise(b, a.inv_spp);
+        out[0] = quantise(rg.x, a.inv_spp); out[1] = quantise(rg.y, a.inv_spp); out[2] = quantise(b, a.inv_spp);
     }
 }
 

@@ -10,8 +10,8 @@
 //                   start the next sample / take the next unit): full lanes where the megakernel runs 5-12 of 32
 //     wf_decide     one thread: loop again while any slot is alive; resets the queue counters
 //
-// Every slot sums its unit's samples in order exactly like a megakernel lane, so both variants write bit-identical
-// partial sums.  State: 88 bytes per slot (SoA), ~2.4 M slots.
+// Finished samples go to the same fixed-point pixel accumulators as the megakernel's, so both variants produce
+// bit-identical images.  State: 72 bytes per slot (SoA), ~2.4 M slots.
 #pragma once
 #include "r1_kernels.cuh"
 
@@ -28,7 +28,6 @@ struct WfState {
     float4 *ray_o;      // origin.xyz, -
     float4 *ray_d;      // dir.xyz, -
     float4 *thr;        // throughput.rgb, depth (int bits)
-    float4 *acc;        // unit accumulator.rgb, -
     uint4 *meta;        // unit (kDead = slot retired), sample index, rng key, rng ctr
     float *hit_t;
     int32_t *hit_idx;
@@ -71,12 +70,11 @@ __global__ void __launch_bounds__(256) wf_init(const __grid_constant__ RenderArg
     }
     for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < w.n_slots; slot += gridDim.x * blockDim.x) {
         if (slot < a.n_units) {
-            uint32_t pixel; float fx, fy; int s, s_end;
-            unit_begin(a, slot, pixel, fx, fy, s, s_end);
+            uint32_t lp, pixel; float fx, fy; int s, s_end;
+            unit_begin(a, slot, lp, pixel, fx, fy, s, s_end);
             Rng rng; f3 o, d;
             primary_ray(a, pixel, fx, fy, s, rng, o, d);
             wf_store_path(w, slot, o, d, mk3(1, 1, 1), 0, slot, s, rng);
-            w.acc[slot] = make_float4(0, 0, 0, 0);
             w.alive[0][slot] = slot;
         } else {
             w.meta[slot] = make_uint4(kDead, 0, 0, 0);
@@ -166,7 +164,7 @@ __global__ void __launch_bounds__(256) wf_shade(const __grid_constant__ RenderAr
         bool ended = false, alive = false;
         uint32_t slot = 0, unit = 0;
         int s = 0, depth = 0;
-        f3 o = mk3(0, 0, 0), d = mk3(0, 0, 0), thr = mk3(1, 1, 1), acc = mk3(0, 0, 0);
+        f3 o = mk3(0, 0, 0), d = mk3(0, 0, 0), thr = mk3(1, 1, 1), contrib = mk3(0, 0, 0);
         Rng rng; rng.key = 0; rng.ctr = 0;
         if (valid) {
             slot = w.queue[(size_t)c * w.n_slots + j];
@@ -176,24 +174,16 @@ __global__ void __launch_bounds__(256) wf_shade(const __grid_constant__ RenderAr
             unit = m.x; s = (int)m.y; rng.key = m.z; rng.ctr = m.w;
             const int hit = w.hit_idx[slot];
             const float4 e = hit >= 0 ? __ldg(a.scene.exact + hit) : make_float4(0, 0, 0, 0);
-            f3 contrib;
             ended = shade_step(a, hit, w.hit_t[slot], e, o, d, thr, depth, rng, contrib);
             alive = true;
-            if (ended) {
-                const float4 ac = w.acc[slot];
-                acc = add3(mk3(ac.x, ac.y, ac.z), contrib);
-                ++s;
-            }
         }
-        // path ended: next sample of the unit, or store the unit and take the next one (warp-aggregated atomic)
-        uint32_t pixel; float fx, fy; int s0, s_end;
+        // path ended: add the sample to its pixel, then the next sample of the unit or the next unit (warp-aggregated atomic)
+        uint32_t lp, pixel; float fx, fy; int s0, s_end;
         bool want_unit = false;
         if (ended) {
-            unit_begin(a, unit, pixel, fx, fy, s0, s_end);
-            if (s == s_end) {
-                a.partial[unit] = make_float4(acc.x, acc.y, acc.z, 0.0f);
-                want_unit = true;
-            }
+            unit_begin(a, unit, lp, pixel, fx, fy, s0, s_end);
+            accumulate_sample(a, lp, contrib);
+            want_unit = ++s == s_end;
         }
         const unsigned need = __ballot_sync(kFull, want_unit);
         if (need) {
@@ -203,8 +193,7 @@ __global__ void __launch_bounds__(256) wf_shade(const __grid_constant__ RenderAr
             base = __shfl_sync(kFull, base, leader);
             if (want_unit) {
                 unit = base + __popc(need & ((1u << lane) - 1u));
-                acc = mk3(0, 0, 0);
-                if (unit < a.n_units) unit_begin(a, unit, pixel, fx, fy, s, s_end);
+                if (unit < a.n_units) unit_begin(a, unit, lp, pixel, fx, fy, s, s_end);
                 else { alive = false; unit = kDead; }
             }
         }
@@ -214,7 +203,6 @@ __global__ void __launch_bounds__(256) wf_shade(const __grid_constant__ RenderAr
                 thr = mk3(1, 1, 1);
                 depth = 0;
             }
-            if (ended) w.acc[slot] = make_float4(acc.x, acc.y, acc.z, 0.0f);
             if (alive) wf_store_path(w, slot, o, d, thr, depth, unit, s, rng);
             else w.meta[slot] = make_uint4(kDead, 0, 0, 0);
         }
@@ -261,7 +249,7 @@ inline int wavefront_render(WavefrontBuffers &b, const RenderArgs &a, int sm_cou
     WfState w;
     w.n_slots = wavefront_slots(a.n_units, sm_count);
     const size_t n = w.n_slots;
-    const size_t bytes = n * (16 * 4 + 16 + 4 + 4 + 16 + 8) + 64 + 256;
+    const size_t bytes = n * (16 * 3 + 16 + 4 + 4 + 16 + 8) + 64 + 256;
     if (bytes > b.pool_bytes) {
         if (b.pool) cudaFree(b.pool);
         b.pool = nullptr; b.pool_bytes = 0;
@@ -272,7 +260,6 @@ inline int wavefront_render(WavefrontBuffers &b, const RenderArgs &a, int sm_cou
     w.ray_o = reinterpret_cast<float4 *>(p); p += n * 16;
     w.ray_d = reinterpret_cast<float4 *>(p); p += n * 16;
     w.thr = reinterpret_cast<float4 *>(p); p += n * 16;
-    w.acc = reinterpret_cast<float4 *>(p); p += n * 16;
     w.meta = reinterpret_cast<uint4 *>(p); p += n * 16;
     w.queue = reinterpret_cast<uint32_t *>(p); p += n * 16;
     w.hit_t = reinterpret_cast<float *>(p); p += n * 4;

@@ -133,6 +133,12 @@ int r1_scatter(r1_scene *scene, int n, const float *dir_in, const float *p, cons
                const float *rand_sphere, const float *rand_u, int32_t *ok, float *atten, float *dir_out);
 /* Camera::getRay (rayweek1.cpp:381-386) with the lens-disk sample injected (disk: 2 per ray). */
 int r1_get_ray(r1_scene *scene, int n, const float *su, const float *tv, const float *disk, float *org, float *dir);
+/* Replay (parity): the pixel loop of render_tile (rayweek1.cpp:752-765) for n pixels, one per thread, driven by the
+ * REFERENCE's xorshift streams from the given states (state: scalar stream, state4: the four lanes of the x4 stream) with
+ * its rejection loops, through the production scan / scatter code.  color_sum = float radiance summed over spp samples
+ * (3 per pixel), num_rays = color() calls per pixel.  Compared with recorded runs of the reference's own color(). */
+int r1_replay_pixels(r1_scene *scene, int n, const int32_t *xy, int width, int height, int spp, int max_bounces,
+                     const uint32_t *state, const uint32_t *state4, float *color_sum, uint32_t *num_rays);
 /* First `n` draws of the counter-based generator for (pixel, sample, seed): raw u32 -- for distribution tests. */
 int r1_rng_draws(uint32_t pixel, uint32_t sample, uint32_t seed, int n, uint32_t *out);
 /* FP32 FMA throughput microbenchmark on `device`: independent FFMA chains (packed = 0) or FFMA2 (packed = 1).

@@ -8,6 +8,8 @@ Everything it writes is small and committed, because /root/reference does not tr
   tests/golden/rays_<scene>.npz    ray segments recorded from real paths walked with the reference's camera,
                                    Hitable::hit and Material::scatter (+ the random inputs each scatter consumed),
                                    plus hand-made edge rays answered by Hitable::hit
+  tests/golden/replay_<scene>.npz  per-pixel replay: generator states before each of 4096 pixels and the float colour the
+                                   reference's own color() returned for it (spp = 1)
   tests/golden/render_<scene>.npz  reference render (its own TileRenderScheduler + render_tile) at 320x180 and
                                    REF_SPP samples per pixel, with the ray count
   tests/golden/ref_stats.json      rays-per-sample of the reference at the default 1280x720x250 workload
@@ -31,6 +33,7 @@ from cpu_checkers import REF_EXE, RefLib  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 N_SEGMENTS = 3072
+N_REPLAY = 4096
 RENDER_W, RENDER_H = 320, 180
 
 
@@ -111,6 +114,13 @@ def main():
         np.savez_compressed(os.path.join(GOLD, "rays_%s.npz" % name), **out)
         print(name, "segments", len(rec["t"]), "hits", int((rec["index"] >= 0).sum()), "edge rays", len(et),
               "edge hits", int((ei >= 0).sum()))
+        # per-pixel replay fixtures: generator states before each pixel + the reference's own colour sums (spp = 1: every
+        # pixel is one independent sample, so a flipped float decision cannot leak into other pixels)
+        prng = np.random.default_rng(77 + len(name))
+        xy = np.stack([prng.integers(0, 1280, N_REPLAY), prng.integers(0, 720, N_REPLAY)], 1).astype(np.int32)
+        st, st4, col, rays_px = ref.replay_pixels(s, xy, 1280, 720, 1)
+        np.savez_compressed(os.path.join(GOLD, "replay_%s.npz" % name), xy=xy, state=st, state4=st4, color=col, rays=rays_px)
+        print("  replay: %d pixels, %.3f rays/sample" % (N_REPLAY, rays_px.mean()))
         if not args.skip_render:
             rgb, rays, el = ref.render(s, RENDER_W, RENDER_H, args.spp)
             np.savez_compressed(os.path.join(GOLD, "render_%s.npz" % name), rgb=rgb, spp=args.spp, num_rays=rays)

@@ -619,6 +619,34 @@ ORC_API uint64_t orc_render(const orc_scene *s, uint8_t *rgb, int w, int h, int 
     return num_rays;
 }
 
+/* Per-pixel replay: the pixel loop of render_tile (:752-765) for ONE pixel from given generator
+ * states -- jitter from the x4 stream, lens disk from the scalar stream, color() -- returning the float radiance sum over
+ * spp samples and the rays traced.  Counterpart of ref_replay_pixels in oracle/ref_harness.cpp and of r1_replay_pixels. */
+ORC_API void orc_replay_pixels(const orc_scene *s, int n, const int32_t *xy, int image_w, int image_h, int spp, int max_bounces,
+                               const uint32_t *state_in, const uint32_t *state4_in, float *color_sum, uint32_t *rays_out)
+{
+    const float inv_w = 1.0f / image_w, inv_h = 1.0f / image_h;
+    for (int k = 0; k < n; ++k) {
+        thread_data td;
+        memset(&td, 0, sizeof(td));
+        td.scene = s; td.max_bounces = max_bounces;
+        td.state = state_in[k];
+        memcpy(td.state4, state4_in + 4 * k, 16);
+        v3 col = v3_make(0, 0, 0);
+        for (int smp = 0; smp < spp; ++smp) {
+            float xi[4], dx, dy;
+            myrand01_x4(td.state4, xi);
+            float u = (xi[0] + (float)xy[2 * k]) * inv_w, v = (xi[1] + (float)xy[2 * k + 1]) * inv_h;
+            random_in_unit_disk(&td.state, &dx, &dy);
+            v3 o, d;
+            camera_ray(s, u, v, dx, dy, &o, &d);
+            col = v3_add(col, color(o, d, &td));
+        }
+        color_sum[3 * k] = col.x; color_sum[3 * k + 1] = col.y; color_sum[3 * k + 2] = col.z;
+        rays_out[k] = (uint32_t)td.num_rays;
+    }
+}
+
 /* ------------------------------------------------------------------ RNG known-answer entry points */
 
 ORC_API uint32_t orc_xorshift32(uint32_t *state) { return xorshift32(state); }

@@ -159,6 +159,36 @@ REF_API int ref_record_paths(const ref_scene *h, int max_segments, int image_w, 
     return n;
 }
 
+// Per-pixel replay fixtures: the pixel loop of render_tile (rayweek1.cpp:752-765) around the
+// reference's OWN myrand01_x4 / Camera::getRay / color(), one pixel at a time.  For every pixel it records the two
+// generator states BEFORE the pixel and the float radiance sum AFTER its spp samples, so that another implementation can
+// replay each pixel independently from the same states (in the reference one flipped decision derails the shared
+// sequential streams for every later pixel; recorded states confine it to one pixel).
+REF_API void ref_replay_pixels(const ref_scene *h, int n, const int32_t *xy, int image_w, int image_h, int spp, uint32_t seed,
+                               uint32_t *state_out, uint32_t *state4_out, float *color_sum, uint32_t *rays_out)
+{
+    ThreadData td;
+    memset(&td, 0, sizeof(td));
+    td.scene = h->scene;
+    td.state = seed * 2u + 10001u;
+    td.state4 = _mm_set_epi32(seed + 10001, seed + 10003, seed + 10005, seed + 10007);
+    const Vec3 inv_image_size(1.0f / image_w, 1.0f / image_h, 0);
+    for (int k = 0; k < n; ++k) {
+        state_out[k] = td.state;
+        _mm_storeu_si128((__m128i *)(state4_out + 4 * k), td.state4);
+        const uint64_t rays_before = td.out_num_rays;
+        Vec3 col(0, 0, 0);
+        const Vec3 xyv((float)xy[2 * k], (float)xy[2 * k + 1], 0);
+        for (int s = 0; s < spp; ++s) {
+            Vec3 uv = (Vec3(myrand01_x4(td.state4)) + xyv) * inv_image_size;      // rayweek1.cpp:759
+            Ray r = h->scene->camera.getRay(uv.getX(), uv.getY(), td.state);      // :760
+            col += color(r, h->scene->hitables, 0, &td);                           // :762
+        }
+        put3(color_sum + 3 * k, col);
+        rays_out[k] = (uint32_t)(td.out_num_rays - rays_before);
+    }
+}
+
 // Camera::getRay with the disk sample recovered by replay (see ref_record_paths).
 REF_API void ref_get_ray(const ref_scene *h, int n, const float *su, const float *tv, uint32_t seed, float *disk, float *org, float *dir)
 {

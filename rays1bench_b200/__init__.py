@@ -76,6 +76,7 @@ def _load():
         "r1_trace_rays": (ci, [vp, ci, f32p, f32p, cf, cf, ci, i32p, f32p, f32p, f32p]),
         "r1_scatter": (ci, [vp, ci, f32p, f32p, f32p, i32p, f32p, f32p, i32p, f32p, f32p]),
         "r1_get_ray": (ci, [vp, ci, f32p, f32p, f32p, f32p, f32p]),
+        "r1_replay_pixels": (ci, [vp, ci, i32p, ci, ci, ci, ci, u32p, u32p, f32p, u32p]),
         "r1_rng_draws": (ci, [C.c_uint32, C.c_uint32, C.c_uint32, ci, u32p]),
         "r1_fma_peak": (ci, [ci, ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "r1_host_configure": (ci, [ci, ci, ci, ci, ci, ci, C.c_uint32]),
@@ -201,6 +202,16 @@ class Scene:
         _check(lib.r1_scatter(self.handle, n, c(dir_in), c(p), c(normal), c(index, np.int32), c(rand_sphere), c(rand_u), ok, atten, dout),
                "r1_scatter")
         return ok, atten, dout
+
+    def replay_pixels(self, xy, width, height, spp, state, state4, max_bounces=MAX_BOUNCES):
+        """r1_replay_pixels: per-pixel radiance sums driven by the reference's xorshift streams from recorded states."""
+        n = len(xy)
+        col = np.zeros((n, 3), np.float32)
+        rays = np.zeros(n, np.uint32)
+        _check(lib.r1_replay_pixels(self.handle, n, np.ascontiguousarray(xy, np.int32).reshape(-1), width, height, spp, max_bounces,
+                                    np.ascontiguousarray(state, np.uint32), np.ascontiguousarray(state4, np.uint32).reshape(-1),
+                                    col.reshape(-1), rays), "r1_replay_pixels")
+        return col, rays
 
     def get_ray(self, su, tv, disk):
         n = len(su)

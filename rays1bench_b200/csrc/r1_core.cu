@@ -633,6 +633,28 @@ int r1_get_ray(r1_scene *scene, int n, const float *su, const float *tv, const f
     return R1_OK;
 }
 
+int r1_replay_pixels(r1_scene *scene, int n, const int32_t *xy, int width, int height, int spp, int max_bounces, const uint32_t *state,
+                     const uint32_t *state4, float *color_sum, uint32_t *num_rays)
+{
+    DeviceCtx *cp = nullptr;
+    R1_TRY(get_ctx(scene, &cp));
+    if (n < 0 || width <= 0 || height <= 0 || spp <= 0 || max_bounces < 0 || max_bounces > 50 || (n > 0 && (!xy || !state || !state4 || !color_sum || !num_rays)))
+        return fail(R1_ERR_ARG, "bad argument");
+    if (n == 0) return R1_OK;
+    if (cp->dev.n_pad > r1::kMaxStagedSpheres) return fail(R1_ERR_LIMIT, "r1_replay_pixels stages at most %d spheres", r1::kMaxStagedSpheres);
+    DevBuf a, b, c, d, e;
+    R1_TRY(a.upload(xy, (size_t)n * 8)); R1_TRY(b.upload(state, (size_t)n * 4)); R1_TRY(c.upload(state4, (size_t)n * 16));
+    R1_TRY(d.alloc((size_t)n * 12)); R1_TRY(e.alloc((size_t)n * 4));
+    const size_t smem = 16 + (size_t)cp->dev.n_pad * 32;
+    R1_CUDA(cudaFuncSetAttribute(r1::replay_pixels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    r1::replay_pixels_kernel<<<(n + 127) / 128, 128, smem>>>(cp->dev, n, a.as<int32_t>(), width, height, spp, max_bounces, b.as<uint32_t>(), c.as<uint32_t>(),
+                                                            d.as<float>(), e.as<uint32_t>());
+    R1_CUDA(cudaGetLastError());
+    R1_CUDA(cudaDeviceSynchronize());
+    R1_TRY(d.download(color_sum, (size_t)n * 12)); R1_TRY(e.download(num_rays, (size_t)n * 4));
+    return R1_OK;
+}
+
 int r1_rng_draws(uint32_t pixel, uint32_t sample, uint32_t seed, int n, uint32_t *out)
 {
     if (n < 0 || (n > 0 && !out)) return fail(R1_ERR_ARG, "bad argument");

@@ -332,6 +332,88 @@ __global__ void rng_kernel(uint32_t pixel, uint32_t sample, uint32_t seed, int n
     }
 }
 
+// ------------------------------------------------------------------------------------------------ replay (parity)
+// the pixel loop of render_tile (rayweek1.cpp:752-765) for one pixel per thread, driven by the
+// REFERENCE's generators from recorded states instead of the counter-based RNG: xorshift32 13/17/15 (mymath.h:17-25), the
+// x4 stream for jitter and the unit-ball rejection loop (mymath.h:41-73, 224-235), the scalar stream for the lens-disk
+// rejection loop and the dielectric coin (rayweek1.cpp:353-362, 503).  Everything else -- camera_ray, scan, exact test,
+// hit_finalise, scatter, sky -- is the production device code, so this compares the GPU integrator with the reference's
+// color() sample by sample.  Attenuations are multiplied innermost-first like the recursion (rayweek1.cpp:525).
+struct RefRng {
+    uint32_t state, s4[4];
+    __device__ __forceinline__ static uint32_t step(uint32_t &x) { x ^= x << 13; x ^= x >> 17; x ^= x << 15; return x; }
+    __device__ __forceinline__ float rand01() { return fmul((float)(step(state) & 0xFFFFFFu), 5.9604644775390625e-8f); }
+    __device__ __forceinline__ float rand02() { return __fdiv_rn((float)(step(state) & 0xFFFFFFu), 8388608.0f); }
+    __device__ __forceinline__ void rand_x4(float scale, float (&out)[4])
+    {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) out[k] = fmul((float)(int)(step(s4[k]) & 0xFFFFFFu), scale);
+    }
+};
+
+__global__ void __launch_bounds__(128) replay_pixels_kernel(const __grid_constant__ DevScene sc, int n, const int32_t *xy, int image_w, int image_h,
+                                                            int spp, int max_bounces, const uint32_t *state_in, const uint32_t *state4_in,
+                                                            float *color_sum, uint32_t *rays_out)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4 *s_spheres = reinterpret_cast<float4 *>(smem_raw + 16);
+    stage_spheres(sc, s_spheres, reinterpret_cast<uint64_t *>(smem_raw));
+    const float4 *s_scan = s_spheres, *s_exact = s_spheres + sc.n_pad;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    RefRng rng;
+    rng.state = state_in[k];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rng.s4[j] = state4_in[4 * k + j];
+    const float inv_w = 1.0f / image_w, inv_h = 1.0f / image_h;
+    const float fx = (float)xy[2 * k], fy = (float)xy[2 * k + 1];
+    f3 col = mk3(0, 0, 0);
+    uint32_t rays = 0;
+    for (int smp = 0; smp < spp; ++smp) {
+        float xi[4];
+        rng.rand_x4((float)(1.0 / 16777216.0), xi);                                   // myrand01_x4, lanes 0 and 1 (:759)
+        const float u = fmul(fadd(xi[0], fx), inv_w), v = fmul(fadd(xi[1], fy), inv_h);
+        float px, py;
+        do {                                                                           // random_in_unit_disk: first draw lands in y (gcc)
+            py = fsub(rng.rand02(), 1.0f);
+            px = fsub(rng.rand02(), 1.0f);
+        } while (fadd(fmul(px, px), fmul(py, py)) >= 1.0f);
+        f3 o, d;
+        camera_ray(sc.cam, u, v, px, py, o, d);
+        f3 stack[51];
+        int depth = 0;
+        f3 leaf = mk3(0, 0, 0);
+        for (;;) {
+            ++rays;
+            float t = kTMax;
+            int hit = -1;
+            scan<true>(s_scan, s_exact, sc.n8, o, d, kTMin, t, hit);
+            if (hit < 0) { leaf = sky(d); break; }
+            if (depth >= max_bounces) break;
+            f3 p, nrm, atten, nd, rs = mk3(0, 0, 0);
+            float ru = 0.0f;
+            hit_finalise(s_exact[hit], sc.inv_radius[hit], o, d, t, p, nrm);
+            const int kind = sc.kind[hit];
+            if (kind == 2) {
+                ru = rng.rand01();                                                     // Dielectric: one scalar draw (:503)
+            } else {
+                float r4[4];
+                do {                                                                   // random_in_unit_sphere on the x4 stream
+                    rng.rand_x4((float)(1.0 / 8388608.0), r4);
+                    rs = mk3(fsub(r4[0], 1.0f), fsub(r4[1], 1.0f), fsub(r4[2], 1.0f));
+                } while (fadd(fadd(fmul(rs.x, rs.x), fmul(rs.y, rs.y)), fmul(rs.z, rs.z)) >= 1.0f);
+            }
+            if (!scatter(kind, sc.mat[hit], d, p, nrm, rs, ru, atten, nd)) break;
+            stack[depth++] = atten;
+            o = p; d = nd;
+        }
+        while (depth > 0) { --depth; leaf = mk3(fmul(stack[depth].x, leaf.x), fmul(stack[depth].y, leaf.y), fmul(stack[depth].z, leaf.z)); }
+        col = add3(col, leaf);
+    }
+    color_sum[3 * k] = col.x; color_sum[3 * k + 1] = col.y; color_sum[3 * k + 2] = col.z;
+    rays_out[k] = rays;
+}
+
 // ------------------------------------------------------------------------------------------------ FP32 peak
 // 16 independent accumulator chains per thread; packed = FFMA2 on float2 accumulators.  FLOPs = 2 per FMA.
 template <bool kPacked>

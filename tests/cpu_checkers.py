@@ -140,6 +140,7 @@ class Oracle(_Checker):
         L = self.lib
         L.orc_scatter.argtypes = [C.c_void_p, C.c_int, _fp, _fp, _fp, _ip, _fp, _fp, _ip, _fp, _fp]
         L.orc_get_ray.argtypes = [C.c_void_p, C.c_int, _fp, _fp, _fp, _fp, _fp]
+        L.orc_replay_pixels.argtypes = [C.c_void_p, C.c_int, _ip, C.c_int, C.c_int, C.c_int, C.c_int, _up, _up, _fp, _up]
         L.orc_render.restype = C.c_uint64
         L.orc_render.argtypes = [C.c_void_p, _bp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
 
@@ -160,6 +161,14 @@ class Oracle(_Checker):
         self.lib.orc_get_ray(s, n, np.ascontiguousarray(su, _f), np.ascontiguousarray(tv, _f),
                              np.ascontiguousarray(disk, _f), org, d)
         return org, d
+
+    def replay_pixels(self, s, xy, w, h, spp, state, state4, max_bounces=50):
+        n = len(xy)
+        col = np.zeros((n, 3), _f)
+        rays = np.zeros(n, np.uint32)
+        self.lib.orc_replay_pixels(s, n, np.ascontiguousarray(xy, np.int32), w, h, spp, max_bounces, np.ascontiguousarray(state, np.uint32),
+                                   np.ascontiguousarray(state4, np.uint32), col, rays)
+        return col, rays
 
     def render(self, s, w, h, spp, max_bounces=50, threads=0):
         """threads <= 0: the reference's single-thread branch (deterministic seeds, rayweek1.cpp:880-881)."""
@@ -184,6 +193,7 @@ class RefLib(_Checker):
         L.ref_render.restype = C.c_uint64
         L.ref_render.argtypes = [C.c_void_p, _bp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
         L.ref_hardware_concurrency.restype = C.c_int
+        L.ref_replay_pixels.argtypes = [C.c_void_p, C.c_int, _ip, C.c_int, C.c_int, C.c_int, C.c_uint32, _up, _up, _fp, _up]
 
     def record_paths(self, s, n, w=1280, h=720, seed=1):
         a = dict(org=np.zeros((n, 3), _f), dir=np.zeros((n, 3), _f), depth=np.zeros(n, np.int32),
@@ -203,6 +213,16 @@ class RefLib(_Checker):
         d = np.zeros((n, 3), _f)
         self.lib.ref_get_ray(s, n, np.ascontiguousarray(su, _f), np.ascontiguousarray(tv, _f), seed, disk, org, d)
         return disk, org, d
+
+    def replay_pixels(self, s, xy, w, h, spp, seed=5):
+        """-> (state[n], state4[n,4] before each pixel, float colour sum[n,3], rays[n])"""
+        n = len(xy)
+        state = np.zeros(n, np.uint32)
+        state4 = np.zeros((n, 4), np.uint32)
+        col = np.zeros((n, 3), _f)
+        rays = np.zeros(n, np.uint32)
+        self.lib.ref_replay_pixels(s, n, np.ascontiguousarray(xy, np.int32), w, h, spp, seed, state, state4, col, rays)
+        return state, state4, col, rays
 
     def render(self, s, w, h, spp, threads=0):
         """threads <= 0: std::thread::hardware_concurrency(), as benchmark() does (rayweek1.cpp:869)."""

@@ -34,7 +34,7 @@ struct WfState {
     uint32_t *queue;    // 4 classes x n_slots slot indices
     uint32_t *alive[2]; // compacted lists of live slots: intersect reads alive[parity], shade fills alive[parity ^ 1]
     uint32_t *counters; // [0..3] class queue lengths, [4] live slots after shade, [5] loop iterations so far,
-                        // [6] parity, [7] length of alive[parity]
+                        // [6] parity, [7] length of alive[parity], [8] next tile of wf_intersect
     uint32_t n_slots;
 };
 
@@ -91,12 +91,17 @@ __global__ void __launch_bounds__(kWfThreads, 1) wf_intersect(const __grid_const
     stage_spheres(a.scene, s_spheres, reinterpret_cast<uint64_t *>(smem_raw));
     const float4 *s_scan = s_spheres, *s_exact = s_spheres + a.scene.n_pad;
     const unsigned lane = threadIdx.x & 31u;
-    const uint32_t warps = (gridDim.x * blockDim.x) >> 5, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t n_alive = w.counters[7];
     const uint32_t *alive = w.alive[w.counters[6] & 1u];
     const uint32_t n_tiles = (n_alive + 32 * R - 1) / (32 * R);
     uint32_t nrays = 0;
-    for (uint32_t tile = warp; tile < n_tiles; tile += warps) {
+    for (;;) {
+        // tiles are handed out dynamically (one atomic per warp per 32 * R rays): the exact-candidate work per tile varies, and a
+        // static split left the SMs idle for 30 % of the kernel
+        uint32_t tile = 0;
+        if (lane == 0) tile = atomicAdd(&w.counters[8], 1u);
+        tile = __shfl_sync(kFull, tile, 0);
+        if (tile >= n_tiles) break;
         f3 o[R], d[R];
         float t[R];
         int hit[R];
@@ -223,6 +228,7 @@ __global__ void wf_decide(const __grid_constant__ WfState w, cudaGraphConditiona
 {
     const uint32_t alive = w.counters[4];
     for (int k = 0; k < 5; ++k) w.counters[k] = 0;
+    w.counters[8] = 0;                                      // wf_intersect's tile counter
     w.counters[5] += 1;
     w.counters[6] ^= 1u;
     w.counters[7] = alive;

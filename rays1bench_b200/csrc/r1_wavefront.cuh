@@ -11,7 +11,7 @@
 //     wf_decide     one thread: loop again while any slot is alive; resets the queue counters
 //
 // Finished samples go to the same fixed-point pixel accumulators as the megakernel's, so both variants produce
-// bit-identical images.  State: 72 bytes per slot (SoA), ~2.4 M slots.
+// bit-identical images.  State: one 64-byte record per slot, ~2.4 M slots.
 #pragma once
 #include "r1_kernels.cuh"
 
@@ -24,13 +24,13 @@ constexpr int kWfRays = 4;          // rays per lane in wf_intersect
 constexpr int kWfThreads = 512;     // 128 registers per thread, one CTA per SM
 constexpr uint32_t kDead = 0xffffffffu;
 
+// One 64-byte record per slot (two 32-byte sectors): intersect touches the first sector only, shade reads and writes both.
+//   [0] origin.xyz, hit t      [1] dir.xyz, hit sphere index (int bits)
+//   [2] throughput.rgb, depth (int bits)      [3] unit (kDead = slot retired), sample index, rng key, rng ctr  (uint bits)
+// (The first layout kept six separate SoA arrays: wf_shade, which visits slots in class-queue order, then moved six
+// scattered sectors per ray in each direction and took 90 ms per frame.)
 struct WfState {
-    float4 *ray_o;      // origin.xyz, -
-    float4 *ray_d;      // dir.xyz, -
-    float4 *thr;        // throughput.rgb, depth (int bits)
-    uint4 *meta;        // unit (kDead = slot retired), sample index, rng key, rng ctr
-    float *hit_t;
-    int32_t *hit_idx;
+    float4 *slots;      // 4 float4 per slot
     uint32_t *queue;    // 4 classes x n_slots slot indices
     uint32_t *alive[2]; // compacted lists of live slots: intersect reads alive[parity], shade fills alive[parity ^ 1]
     uint32_t *counters; // [0..3] class queue lengths, [4] live slots after shade, [5] loop iterations so far,
@@ -54,10 +54,15 @@ inline void wavefront_free(WavefrontBuffers &b)
 
 __device__ __forceinline__ void wf_store_path(const WfState &w, uint32_t slot, f3 o, f3 d, f3 thr, int depth, uint32_t unit, int s, const Rng &rng)
 {
-    w.ray_o[slot] = make_float4(o.x, o.y, o.z, 0.0f);
-    w.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.0f);
-    w.thr[slot] = make_float4(thr.x, thr.y, thr.z, __int_as_float(depth));
-    w.meta[slot] = make_uint4(unit, (uint32_t)s, rng.key, rng.ctr);
+    float4 *rec = w.slots + (size_t)slot * 4;
+    rec[0] = make_float4(o.x, o.y, o.z, 0.0f);
+    rec[1] = make_float4(d.x, d.y, d.z, __int_as_float(-1));
+    rec[2] = make_float4(thr.x, thr.y, thr.z, __int_as_float(depth));
+    rec[3] = make_float4(__uint_as_float(unit), __uint_as_float((uint32_t)s), __uint_as_float(rng.key), __uint_as_float(rng.ctr));
+}
+__device__ __forceinline__ void wf_retire(const WfState &w, uint32_t slot)
+{
+    w.slots[(size_t)slot * 4 + 3] = make_float4(__uint_as_float(kDead), 0.0f, 0.0f, 0.0f);
 }
 
 // slot i starts unit i (the unit counter is preset to min(n_slots, n_units))
@@ -77,7 +82,7 @@ __global__ void __launch_bounds__(256) wf_init(const __grid_constant__ RenderArg
             wf_store_path(w, slot, o, d, mk3(1, 1, 1), 0, slot, s, rng);
             w.alive[0][slot] = slot;
         } else {
-            w.meta[slot] = make_uint4(kDead, 0, 0, 0);
+            wf_retire(w, slot);
         }
     }
 }
@@ -114,7 +119,7 @@ __global__ void __launch_bounds__(kWfThreads, 1) wf_intersect(const __grid_const
             slots[r] = live[r] ? alive[i] : 0u;
             o[r] = mk3(0.0f, 1.0e18f, 0.0f); d[r] = mk3(0.0f, 0.0f, 0.0f);   // lanes past the end scan a ray that passes no filter
             if (live[r]) {
-                const float4 ro = w.ray_o[slots[r]], rd = w.ray_d[slots[r]];
+                const float4 ro = w.slots[(size_t)slots[r] * 4], rd = w.slots[(size_t)slots[r] * 4 + 1];
                 o[r] = mk3(ro.x, ro.y, ro.z); d[r] = mk3(rd.x, rd.y, rd.z);
             }
             t[r] = kTMax; hit[r] = -1;
@@ -126,8 +131,8 @@ __global__ void __launch_bounds__(kWfThreads, 1) wf_intersect(const __grid_const
             int cls = -1;
             if (live[r]) {
                 ++nrays;
-                w.hit_t[slot] = t[r];
-                w.hit_idx[slot] = hit[r];
+                w.slots[(size_t)slot * 4].w = t[r];                       // same 32-byte sector as the ray
+                w.slots[(size_t)slot * 4 + 1].w = __int_as_float(hit[r]);
                 cls = hit[r] < 0 ? 0 : 1 + __ldg(a.scene.kind + hit[r]);
             }
 #pragma unroll
@@ -173,13 +178,13 @@ __global__ void __launch_bounds__(256) wf_shade(const __grid_constant__ RenderAr
         Rng rng; rng.key = 0; rng.ctr = 0;
         if (valid) {
             slot = w.queue[(size_t)c * w.n_slots + j];
-            const float4 ro = w.ray_o[slot], rd = w.ray_d[slot], th = w.thr[slot];
-            const uint4 m = w.meta[slot];
+            const float4 *rec = w.slots + (size_t)slot * 4;
+            const float4 ro = rec[0], rd = rec[1], th = rec[2], m = rec[3];
             o = mk3(ro.x, ro.y, ro.z); d = mk3(rd.x, rd.y, rd.z); thr = mk3(th.x, th.y, th.z); depth = __float_as_int(th.w);
-            unit = m.x; s = (int)m.y; rng.key = m.z; rng.ctr = m.w;
-            const int hit = w.hit_idx[slot];
+            unit = __float_as_uint(m.x); s = (int)__float_as_uint(m.y); rng.key = __float_as_uint(m.z); rng.ctr = __float_as_uint(m.w);
+            const int hit = __float_as_int(rd.w);
             const float4 e = hit >= 0 ? __ldg(a.scene.exact + hit) : make_float4(0, 0, 0, 0);
-            ended = shade_step(a, hit, w.hit_t[slot], e, o, d, thr, depth, rng, contrib);
+            ended = shade_step(a, hit, ro.w, e, o, d, thr, depth, rng, contrib);
             alive = true;
         }
         // path ended: add the sample to its pixel, then the next sample of the unit or the next unit (warp-aggregated atomic)
@@ -209,7 +214,7 @@ __global__ void __launch_bounds__(256) wf_shade(const __grid_constant__ RenderAr
                 depth = 0;
             }
             if (alive) wf_store_path(w, slot, o, d, thr, depth, unit, s, rng);
-            else w.meta[slot] = make_uint4(kDead, 0, 0, 0);
+            else wf_retire(w, slot);
         }
         // live slots go to the next iteration's compacted list (ballot + popc, one atomic per warp)
         const unsigned am = __ballot_sync(kFull, valid && alive);
@@ -255,7 +260,7 @@ inline int wavefront_render(WavefrontBuffers &b, const RenderArgs &a, int sm_cou
     WfState w;
     w.n_slots = wavefront_slots(a.n_units, sm_count);
     const size_t n = w.n_slots;
-    const size_t bytes = n * (16 * 3 + 16 + 4 + 4 + 16 + 8) + 64 + 256;
+    const size_t bytes = n * (64 + 16 + 8) + 64 + 256;
     if (bytes > b.pool_bytes) {
         if (b.pool) cudaFree(b.pool);
         b.pool = nullptr; b.pool_bytes = 0;
@@ -263,13 +268,8 @@ inline int wavefront_render(WavefrontBuffers &b, const RenderArgs &a, int sm_cou
         b.pool_bytes = bytes;
     }
     unsigned char *p = static_cast<unsigned char *>(b.pool);
-    w.ray_o = reinterpret_cast<float4 *>(p); p += n * 16;
-    w.ray_d = reinterpret_cast<float4 *>(p); p += n * 16;
-    w.thr = reinterpret_cast<float4 *>(p); p += n * 16;
-    w.meta = reinterpret_cast<uint4 *>(p); p += n * 16;
+    w.slots = reinterpret_cast<float4 *>(p); p += n * 64;
     w.queue = reinterpret_cast<uint32_t *>(p); p += n * 16;
-    w.hit_t = reinterpret_cast<float *>(p); p += n * 4;
-    w.hit_idx = reinterpret_cast<int32_t *>(p); p += n * 4;
     w.alive[0] = reinterpret_cast<uint32_t *>(p); p += n * 4;
     w.alive[1] = reinterpret_cast<uint32_t *>(p); p += n * 4;
     w.counters = reinterpret_cast<uint32_t *>(p);

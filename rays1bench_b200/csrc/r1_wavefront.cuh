@@ -20,8 +20,8 @@
 
 namespace r1 {
 
-constexpr int kWfRays = 4;          // rays per lane in wf_intersect
-constexpr int kWfThreads = 512;     // 128 registers per thread, one CTA per SM
+constexpr int kWfRays = 2;          // rays per lane in wf_intersect (measured: 4 x 512 threads 3815, 2 x 768 3988, 2 x 1024 4070,
+constexpr int kWfThreads = 1024;    //  1 x 1024 3914 Mrays/s on the large scene -- the candidate loop, not the sphere loads, bounds it)
 constexpr uint32_t kDead = 0xffffffffu;
 
 // One 64-byte record per slot (two 32-byte sectors): intersect touches the first sector only, shade reads and writes both.
@@ -88,8 +88,8 @@ __global__ void __launch_bounds__(256) wf_init(const __grid_constant__ RenderArg
 }
 
 // Hitable::hit for every live slot; R rays per lane; classification + queue compaction.
-template <int R>
-__global__ void __launch_bounds__(kWfThreads, 1) wf_intersect(const __grid_constant__ RenderArgs a, const __grid_constant__ WfState w)
+template <int R, int kThreads>
+__global__ void __launch_bounds__(kThreads, 1) wf_intersect(const __grid_constant__ RenderArgs a, const __grid_constant__ WfState w)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4 *s_spheres = reinterpret_cast<float4 *>(smem_raw + 16);
@@ -282,9 +282,19 @@ inline int wavefront_render(WavefrontBuffers &b, const RenderArgs &a, int sm_cou
     *launches += 1;
 
     const size_t smem = 16 + (size_t)a.scene.n_pad * 32;
-    R1_WF_CUDA(cudaFuncSetAttribute(wf_intersect<kWfRays>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const uint32_t n_tiles = (w.n_slots + 32 * kWfRays - 1) / (32 * kWfRays);
-    const int igrid = (int)std::min<uint32_t>((uint32_t)sm_count, (n_tiles * 32 + kWfThreads - 1) / kWfThreads);
+    // rays per lane / threads per CTA of wf_intersect (R1_WF_CONFIG=R,threads overrides the tuned default for experiments)
+    int cfg_r = kWfRays, cfg_t = kWfThreads;
+    if (const char *env = getenv("R1_WF_CONFIG")) sscanf(env, "%d,%d", &cfg_r, &cfg_t);
+    void (*ikern)(RenderArgs, WfState) = nullptr;
+    if (cfg_r == 4 && cfg_t == 512) ikern = wf_intersect<4, 512>;
+    else if (cfg_r == 2 && cfg_t == 768) ikern = wf_intersect<2, 768>;
+    else if (cfg_r == 2 && cfg_t == 512) ikern = wf_intersect<2, 512>;
+    else if (cfg_r == 2 && cfg_t == 1024) ikern = wf_intersect<2, 1024>;
+    else if (cfg_r == 1 && cfg_t == 1024) ikern = wf_intersect<1, 1024>;
+    else return (int)cudaErrorInvalidValue;
+    R1_WF_CUDA(cudaFuncSetAttribute(ikern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t n_tiles = (w.n_slots + 32 * cfg_r - 1) / (32 * cfg_r);
+    const int igrid = (int)std::min<uint32_t>((uint32_t)sm_count, (n_tiles * 32 + cfg_t - 1) / cfg_t);
     const int sgrid = sm_count * 8;
 
     if (getenv("R1_WF_HOSTLOOP")) {
@@ -298,7 +308,7 @@ inline int wavefront_render(WavefrontBuffers &b, const RenderArgs &a, int sm_cou
         *flag = 1;
         while (*flag) {
             R1_WF_CUDA(cudaEventRecord(ev[0], stream));
-            wf_intersect<kWfRays><<<igrid, kWfThreads, smem, stream>>>(a, w);
+            ikern<<<igrid, cfg_t, smem, stream>>>(a, w);
             R1_WF_CUDA(cudaEventRecord(ev[1], stream));
             wf_shade<<<sgrid, 256, 0, stream>>>(a, w);
             R1_WF_CUDA(cudaEventRecord(ev[2], stream));
@@ -338,7 +348,7 @@ inline int wavefront_render(WavefrontBuffers &b, const RenderArgs &a, int sm_cou
     cudaStream_t cap;
     R1_WF_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
     R1_WF_CUDA(cudaStreamBeginCaptureToGraph(cap, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
-    wf_intersect<kWfRays><<<igrid, kWfThreads, smem, cap>>>(a, w);
+    ikern<<<igrid, cfg_t, smem, cap>>>(a, w);
     wf_shade<<<sgrid, 256, 0, cap>>>(a, w);
     wf_decide<<<1, 1, 0, cap>>>(w, handle, nullptr);
     R1_WF_CUDA(cudaStreamEndCapture(cap, nullptr));

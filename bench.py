@@ -38,9 +38,9 @@ WORKLOADS = {
 }
 METRIC = "Mrays/s (large scene)"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE megakernel launch, from the ncu --set full capture summarised in
-# profiles/r01_ncu_megakernel_large.md (capture D); null for workloads that were not captured
-NCU_TRAFFIC_BYTES = {("large", "mega"): 17382656 + 877844480}  # capture D: the build with float partial sums (58 M x 16 B);
-#                                                                    the fixed-point accumulators since then are 32 B per pixel
+# profiles/r01_ncu_megakernel_large.md (capture E); null for workloads that were not captured
+NCU_TRAFFIC_BYTES = {("large", "mega"): 29593600 + 15104}  # capture E (final round-1 build): the 32-byte fixed-point pixel
+#                                                                accumulators read once after the L2 flush; they stay in L2 after
 NOMINAL_SM_MHZ = 1965.0
 # the reference's own published figure for this metric and configuration (step13, large scene,
 # 1280x720, 250 spp) -- 59.362 Mrays/s on an i9-9900K 8c/16t, README.md:52 of the reference.  CPU hardware, quoted as published.

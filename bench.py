@@ -298,8 +298,8 @@ def main():
     hbm_bytes = W * H * (32 * 2 + 3) + n_pad * 32 * sm_count   # fixed-point accumulators zeroed + written back, RGB8 out, staging
     roofline = {"bound": "fp32_fma", "kernel": "r1::megakernel" if args.variant != "wavefront" else "r1::wf_intersect + wf_shade (graph loop)", "achieved": achieved,
                 "peak": peak_meas, "unit": "TFLOP/s", "frac": achieved / peak_meas,
-                "peak_source": "FFMA/FFMA2 chain microbenchmark on this GPU (r1_fma_peak), per GPU; scalar %.1f / packed %.1f TFLOP/s at ~%.0f MHz" %
-                               (peak_scalar, peak_packed, mhz_est),
+                "peak_source": "FFMA/FFMA2 chain microbenchmark on this GPU (r1_fma_peak), per GPU; scalar %.1f / packed %.1f TFLOP/s (SM clock during the run: see clocks)" %
+                               (peak_scalar, peak_packed),
                 "peak_nominal": peak_nominal, "frac_nominal": achieved / peak_nominal,
                 "flops_per_ray": f_ray, "flops_model": "16 per ray-sphere test (FMA=2) x %d real spheres + 70 shading (SURVEY.md 8d)" % n_real,
                 "traffic": NCU_TRAFFIC_BYTES.get((args.workload, args.variant)) if world == 1 else None,

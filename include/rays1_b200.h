@@ -142,7 +142,9 @@ int r1_replay_pixels(r1_scene *scene, int n, const int32_t *xy, int width, int h
 /* First `n` draws of the counter-based generator for (pixel, sample, seed): raw u32 -- for distribution tests. */
 int r1_rng_draws(uint32_t pixel, uint32_t sample, uint32_t seed, int n, uint32_t *out);
 /* FP32 FMA throughput microbenchmark on `device`: independent FFMA chains (packed = 0) or FFMA2 (packed = 1).
- * Returns TFLOP/s (FMA = 2) in *tflops and the SM clock it ran at in *sm_mhz_est (cycles / elapsed). */
+ * Returns TFLOP/s (FMA = 2) in *tflops.  *sm_mhz_est (optional) = clock64 ticks of one thread / elapsed time: a rough
+ * cross-check only -- on the B200 boxes of this project clock64 did not tick at the SM clock (it read ~300 MHz while
+ * nvidia-smi showed 1965 MHz under the same load), so bench.py reports the nvidia-smi clock instead. */
 int r1_fma_peak(int device, int packed, double *tflops, double *sm_mhz_est);
 
 /* ---- part 2: the reference's host surface, C linkage ------------------------------------------------------------- */

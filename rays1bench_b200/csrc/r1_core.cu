@@ -286,7 +286,7 @@ uint32_t r1_scene_count(const r1_scene *scene) { return scene ? (uint32_t)scene-
 int r1_scene_get_soa(const r1_scene *scene, float *cx, float *cy, float *cz, float *radius_sq, float *inv_radius, int32_t *kind, float *albedo,
                      float *param)
 {
-    if (!scene) return fail(R1_ERR_ARG, "null scene");
+    if (!scene || !cx || !cy || !cz || !radius_sq || !inv_radius || !kind || !albedo || !param) return fail(R1_ERR_ARG, "null argument");
     const size_t n = scene->cx.size();
     memcpy(cx, scene->cx.data(), n * 4); memcpy(cy, scene->cy.data(), n * 4); memcpy(cz, scene->cz.data(), n * 4);
     memcpy(radius_sq, scene->radius_sq.data(), n * 4); memcpy(inv_radius, scene->inv_radius.data(), n * 4);
@@ -318,8 +318,12 @@ int r1_scene_commit(r1_scene *scene, int device)
     if (rc) return rc;
     if (scr->cc_major != 10) return fail(R1_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, scr->cc_major, scr->cc_minor);
 
-    DeviceCtx &c = scene->ctx[device];
-    if (c.device >= 0) free_ctx(c);
+    {   // drop a previous commit to this device first; the new context is published only once the upload succeeded
+        auto prev = scene->ctx.find(device);
+        if (prev != scene->ctx.end()) { free_ctx(prev->second); scene->ctx.erase(prev); }
+        if (scene->current == device) scene->current = -1;
+    }
+    DeviceCtx c;
     c.device = device;
 
     const int n = (int)scene->cx.size();
@@ -359,7 +363,10 @@ int r1_scene_commit(r1_scene *scene, int device)
         }
     }
     R1_CUDA(cudaMalloc(&c.block, bytes));
-    R1_CUDA(cudaMemcpy(c.block, host.data(), bytes, cudaMemcpyHostToDevice));
+    {
+        const cudaError_t e = cudaMemcpy(c.block, host.data(), bytes, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFree(c.block); return fail(R1_ERR_CUDA, "scene upload: %s", cudaGetErrorString(e)); }
+    }
     float4 *d4 = reinterpret_cast<float4 *>(c.block);
     c.dev.scan = d4;
     c.dev.exact = d4 + n_pad;
@@ -370,6 +377,7 @@ int r1_scene_commit(r1_scene *scene, int device)
     c.dev.n8 = (n + 7) / 8 * 8;
     c.dev.n_real = n;
     c.dev.cam = scene->cam;
+    scene->ctx[device] = c;
     scene->current = device;
     return R1_OK;
 }
@@ -677,8 +685,12 @@ int r1_fma_peak(int device, int packed, double *tflops, double *sm_mhz_est)
     DevBuf sink, cyc;
     R1_TRY(sink.alloc(16)); R1_TRY(cyc.alloc(16));
     const int iters = 1 << 16, threads = 256, grid = prop.multiProcessorCount * 8;
-    cudaEvent_t e0, e1;
-    R1_CUDA(cudaEventCreate(&e0)); R1_CUDA(cudaEventCreate(&e1));
+    struct Events {
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        ~Events() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+    } ev;
+    R1_CUDA(cudaEventCreate(&ev.e0)); R1_CUDA(cudaEventCreate(&ev.e1));
+    cudaEvent_t e0 = ev.e0, e1 = ev.e1;
     double best_ms = 1e30, mhz = 0;
     for (int rep = 0; rep < 4; ++rep) {  // first repetition is the warm-up
         R1_CUDA(cudaEventRecord(e0));
@@ -693,7 +705,6 @@ int r1_fma_peak(int device, int packed, double *tflops, double *sm_mhz_est)
         // all 8 x 256-thread CTAs per SM are resident (one wave), so one CTA's cycle count spans the kernel
         if (rep > 0 && ms < best_ms) { best_ms = ms; mhz = (double)cycles / (ms * 1e-3) / 1e6; }
     }
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     const double fmas = (double)grid * threads * (double)iters * 16.0;  // 16 scalar FMAs or 8 packed (= 16) per iteration
     *tflops = 2.0 * fmas / (best_ms * 1e-3) / 1e12;
     if (sm_mhz_est) *sm_mhz_est = mhz;

@@ -446,6 +446,20 @@ int r1_render_device(r1_scene *scene, const r1_render_params *params, void *d_rg
     a.inv_spp = (float)(1.0f / prm.spp);                       // rayweek1.cpp:765
     a.magic_chunks = r1::div_magic((uint32_t)a.n_chunks);
     a.magic_width = r1::div_magic((uint32_t)prm.width);
+    a.magic_row_tile = r1::div_magic((uint32_t)prm.row_tile);
+    // Units per fetch (guided self-scheduling, r1::megakernel).  Measured on B200, Mrays/s full image | 1/8 image (the 8-GPU
+    // partition):            1 unit per fetch        up to 64, shrinking as left / (16 * lanes)      up to 16, left / (4 * lanes)
+    //   large  (488)          5875 | 5870             5879 | 5805                                      5861 | 5437
+    //   medium (48)          23724 | 23210           27411 | 25229                                    26928 | 23044
+    //   small  (8)           27367 | 27579           45336 | 37358                                    43391 | 37023
+    // Ranges held by lanes at the end of a render are a serial tail; single units make one atomic per warp per bounce,
+    // which saturates the counter's L2 line when a scan is only a few hundred instructions.
+    if (c.dev.n8 >= 256) { a.sched_kmax = 1; a.sched_div = 1; }
+    else { a.sched_kmax = 64; a.sched_div = 16; }
+    if (const char *e = getenv("R1_SCHED")) {  // tuning knob: "kmax,div"
+        unsigned k = 0, d = 0;
+        if (sscanf(e, "%u,%u", &k, &d) == 2 && k >= 1 && k <= 4096 && d >= 1 && d <= 1024) { a.sched_kmax = k; a.sched_div = d; }
+    }
     a.rgb = (uint8_t *)d_rgb;
     a.num_rays = (unsigned long long *)d_num_rays;
     a.unit_counter = x.unit_counter;

@@ -28,7 +28,8 @@ struct RenderArgs {
     int32_t samples_per_unit, n_chunks;
     uint32_t seed;                   // Rng::seed_hash(global seed)
     float inv_w, inv_h, inv_spp;
-    uint64_t magic_chunks, magic_width;  // floor(2^64 / d) + 1: exact n / d for 32-bit n via one 64-bit mul-high (0 when d == 1)
+    uint64_t magic_chunks, magic_width, magic_row_tile;  // floor(2^64 / d) + 1: exact n / d for 32-bit n via one 64-bit mul-high (0 when d == 1)
+    uint32_t sched_kmax, sched_div;      // unit ranges: a lane takes min(kmax, max(1, units_left / (lanes * div))) units per fetch
 };
 
 constexpr float kFixedScale = 1099511627776.0f;            // 2^40
@@ -80,8 +81,10 @@ __device__ __forceinline__ void unit_begin(const RenderArgs &a, uint32_t unit, u
 {
     lp = fast_div(unit, a.magic_chunks);
     const uint32_t c = unit - lp * (uint32_t)a.n_chunks;
-    const int lr = (int)fast_div(lp, a.magic_width), x = (int)(lp - (uint32_t)lr * (uint32_t)a.width);
-    const int y = global_row(lr, a.row_tile, a.rank, a.world);
+    const uint32_t lr = fast_div(lp, a.magic_width);
+    const int x = (int)(lp - lr * (uint32_t)a.width);
+    const uint32_t tile = fast_div(lr, a.magic_row_tile);                        // global_row() without the integer divisions
+    const int y = (int)((tile * (uint32_t)a.world + (uint32_t)a.rank) * (uint32_t)a.row_tile + (lr - tile * (uint32_t)a.row_tile));
     pixel = (uint32_t)y * (uint32_t)a.width + (uint32_t)x;
     fx = (float)x; fy = (float)y;
     s = (int)c * a.samples_per_unit;
@@ -166,7 +169,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel(const __gri
     f3 o = mk3(0.0f, 1.0e18f, 0.0f), d = mk3(0.0f, 0.0f, 0.0f);  // idle lanes scan a ray that passes no filter
     Rng rng;
     rng.key = 0; rng.ctr = 0;
-    const uint32_t lanes_x4 = gridDim.x * blockDim.x * 4u;
+    const uint32_t lanes_x4 = gridDim.x * blockDim.x * a.sched_div;
 
     for (;;) {
         // -- take a range of units (warp-aggregated: one atomic per warp per refill round).  Guided self-scheduling:
@@ -178,7 +181,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel(const __gri
             unsigned base = 0, k = 0;
             if ((int)lane == leader) {
                 const uint32_t left = a.n_units > last_base ? a.n_units - last_base : 0u;
-                k = min(16u, max(1u, left / lanes_x4));
+                k = min(a.sched_kmax, max(1u, left / lanes_x4));
                 base = atomicAdd(a.unit_counter, k * (unsigned)__popc(need));
             }
             base = __shfl_sync(kFull, base, leader);

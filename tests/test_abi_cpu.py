@@ -252,3 +252,24 @@ def test_compare_tga_tool(r1, tmp_path):
     compare_tga.write_png(str(tmp_path / "a.png"), got)
     raw = open(tmp_path / "a.png", "rb").read()
     assert raw[:8] == b"\x89PNG\r\n\x1a\n" and b"IDAT" in raw
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints ONE JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(os.path.join(root, "oracle", "_ref", "libref_rays1.so")):
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--cpu-budget", "0.3", "--workload", "small"], capture_output=True, text=True, timeout=300, check=True).stdout
+    lines = [l for l in out.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "Mrays/s" and d["higher_is_better"] is True
+    assert d["metric"] == "Mrays/s (small scene)" and d["config"]["workload"].startswith("small scene 1280x720 250 spp")
+    assert d["value"] > 0 and d["e2e"] == {"value": d["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == d["value"] and "spp" in cb["sample"]
+    assert d["gpu_launches"] == 0 and 1.7 < d["rays_per_sample"] < 1.9   # small scene: 1.798 rays per sample (ref_stats.json)

@@ -160,7 +160,8 @@ def main():
         if rank != 0:
             return
         steps, warmup = args.steps, max(args.warmup, 1)
-        r = cpu_reference(args.workload, args.cpu_budget, steps, warmup)
+        # bounded sample per step, and the whole run (warm-up + steps) within about 2.5 minutes of CPU time
+        r = cpu_reference(args.workload, min(args.cpu_budget, 150.0 / (steps + warmup)), steps, warmup)
         line = {"impl": "reference", "metric": metric_name(args.workload), "value": r["value"], "unit": "Mrays/s", "n_gpus": args.gpus, "steps": steps,
                 "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": r["value"] / PUBLISHED_MRAYS[args.workload] if args.workload in PUBLISHED_MRAYS else None,

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define R1_ABI_VERSION 1
+#define R1_ABI_VERSION 2
 
 enum {
     R1_OK = 0,
@@ -82,6 +82,10 @@ void r1_scene_destroy(r1_scene *scene);
 /* Camera::init (rayweek1.cpp:366-379). */
 int r1_scene_set_camera(r1_scene *scene, const float lookfrom[3], const float lookat[3], const float vup[3], float vfov_deg,
                         float aspect, float aperture, float focus_dist);
+/* Installs the 22 camera constants directly, in the order r1_scene_get_camera returns them.  For callers that already hold
+ * the reference's own constants (its Camera::init is folded at compile time by gcc -ffast-math and differs from the run-time
+ * evaluation above by up to 4 ulp): the per-pixel replay fixtures of tests/golden use it to reproduce primary rays bit for bit. */
+int r1_scene_set_camera_raw(r1_scene *scene, const float cam[22]);
 /* SphereSOA::add (soa_sphere.cpp:70-85): stores radius*radius and radius > 0 ? 1/radius : 0.  Metal's `param` is the
  * fuzz (clamped to <= 1 as the Metal ctor does, rayweek1.cpp:424), Dielectric's the refraction index.  Returns the
  * sphere's index (>= 0) or a negative error. */
@@ -167,12 +171,16 @@ void *r1_host_create_scene_from_file(const char *path, int commit);
 /* The r1_scene inside a host Scene (borrowed). */
 r1_scene *r1_host_scene_handle(void *scene);
 /* benchmark(scene, pixels, write_tga, scene_name) (rayweek1.cpp:845-927): renders, prints the reference's report block,
- * deletes the scene, optionally writes out_<name>.tga (which swaps R/B in `pixels` in place, common.h:108-114). */
-int r1_host_benchmark(void *scene, uint8_t *pixels, int write_tga, const char *scene_name, double *elapsed_seconds,
+ * deletes the scene (in every case, also on error), optionally writes out_<name>.tga (which swaps R/B in `pixels` in place,
+ * common.h:108-114).  `pixels_bytes` is the size of the caller's buffer: R1_ERR_ARG if it is smaller than the configured
+ * width * height * 3.  CUDA / NCCL failures come back as a negative code (the C++ benchmark() of rays1_host.h exits instead,
+ * like the reference's surface without error paths would). */
+int r1_host_benchmark(void *scene, uint8_t *pixels, uint64_t pixels_bytes, int write_tga, const char *scene_name, double *elapsed_seconds,
                       uint64_t *num_rays, double *kernel_ms);
 void r1_host_destroy_scene(void *scene);
-/* tga_write_rgb24 (common.h:86-122): 18-byte header, type 2, 24 bpp, bottom-left origin; swaps R and B in `pixels`. */
-int r1_host_write_tga(const char *filename, int width, int height, uint8_t *pixels);
+/* tga_write_rgb24 (common.h:86-122): 18-byte header, type 2, 24 bpp, bottom-left origin; swaps R and B in `pixels`.
+ * R1_ERR_ARG if pixels_bytes < width * height * 3 or a dimension does not fit the 16-bit header fields. */
+int r1_host_write_tga(const char *filename, int width, int height, uint8_t *pixels, uint64_t pixels_bytes);
 /* log_results (common.h:47-77): out_<scene>.txt = "version|%.3fs|<rays>|%0.3f mrays/s|" averaged over the runs. */
 int r1_host_log_results(const char *version, const char *scene, const double *elapsed_seconds, const uint64_t *num_rays,
                         int num_runs);

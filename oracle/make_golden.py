@@ -7,7 +7,10 @@ Everything it writes is small and committed, because /root/reference does not tr
 
   tests/golden/rays_<scene>.npz    ray segments recorded from real paths walked with the reference's camera,
                                    Hitable::hit and Material::scatter (+ the random inputs each scatter consumed),
-                                   plus hand-made edge rays answered by Hitable::hit
+                                   plus hand-made edge rays answered by Hitable::hit, plus (large, synth4096) rays leaving
+                                   the ior >= 5 dielectric spheres from inside, answered by hit + scatter
+  <scene> = small | medium | large (unmodified src/latest) | synth4096 (BASELINE.json config 5: the same sources with
+  MAX_SPHERES = 4096, oracle/_ref/libref_rays1_4096.so)
   tests/golden/replay_<scene>.npz  per-pixel replay: generator states before each of 4096 pixels and the float colour the
                                    reference's own color() returned for it (spp = 1)
   tests/golden/render_<scene>.npz  reference render (its own TileRenderScheduler + render_tile) at 320x180 and
@@ -90,19 +93,43 @@ def edge_rays(ref, scene, name):
     return np.stack(org).astype(np.float32), np.stack(dr).astype(np.float32)
 
 
+def dielectric_exit_rays(ref, scene, min_ior=5.0, per_sphere=16):
+    """Rays that start INSIDE the high-index dielectric spheres and leave them: Dielectric::scatter's refraction branch with
+    ni_over_nt = ior, where 1 - k^2 (1 - dt^2) amplifies float32 rounding by k^2 (ior up to 24.2 in the large scene,
+    rayweek1.cpp:692).  Real camera paths reach these rarely (6 of 3072 recorded segments)."""
+    rng = np.random.default_rng(4242)
+    soa = ref.scene_soa(scene)
+    sel = np.where((soa["kind"] == 2) & (soa["param"] >= min_ior) & (soa["inv_radius"] > 0))[0]
+    org, dr = [], []
+    for i in sel:
+        c = np.array([soa["cx"][i], soa["cy"][i], soa["cz"][i]], np.float32)
+        rad = 1.0 / soa["inv_radius"][i]
+        for k in range(per_sphere):
+            # half of the rays close to the axis (refraction happens: sin(theta) < 1 / ior), half anywhere inside (mostly
+            # total internal reflection, the discriminant <= 0 branch)
+            off = unit(rng.normal(size=3)) * rad * (rng.uniform(0, 0.9 / soa["param"][i]) if k % 2 == 0 else rng.uniform(0, 0.95))
+            org.append(c + off.astype(np.float32))
+            dr.append(unit(rng.normal(size=3)))
+    return np.stack(org).astype(np.float32), np.stack(dr).astype(np.float32)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--spp", type=int, default=16384)
     ap.add_argument("--skip-render", action="store_true")
     ap.add_argument("--skip-exe", action="store_true")
+    ap.add_argument("--scenes", default="small,medium,large,synth4096")
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
-    ref = RefLib()
+    ref1024, ref4096 = RefLib(), RefLib(4096)
     stats_path = os.path.join(GOLD, "ref_stats.json")
     stats = json.load(open(stats_path)) if os.path.exists(stats_path) else {}
     stats["source"] = "montib/rays1bench src/latest, g++ 13.3 -pthread -ffast-math -O3 -march=x86-64-v3 (oracle/Makefile)"
 
-    for name in ("small", "medium", "large"):
+    stats["source_synth4096"] = ("same sources and flags with MAX_SPHERES = 4096 (rayweek1.cpp:174 patched in a temporary copy, "
+                                "oracle/Makefile) + the 4096-sphere builder of oracle/ref_harness.cpp on the reference's classes")
+    for name in args.scenes.split(","):
+        ref = ref4096 if name == "synth4096" else ref1024
         s = ref.scene_create(name)
         rec = ref.record_paths(s, N_SEGMENTS, seed=3)
         eo, ed = edge_rays(ref, s, name)
@@ -111,6 +138,14 @@ def main():
         out = {("seg_" + k): v for k, v in rec.items()}
         out.update(edge_org=eo, edge_dir=ed, edge_index=ei, edge_t=et, edge_p=ep, edge_normal=en,
                    camera=ref.scene_camera(s), **{("soa_" + k): v for k, v in soa.items()})
+        if name in ("large", "synth4096"):
+            do, dd = dielectric_exit_rays(ref, s)
+            rec_d = ref.hit_scatter(s, do, dd)
+            out.update({("diel_" + k): v for k, v in rec_d.items()})
+            ex = (rec_d["index"] >= 0) & (soa["kind"][np.maximum(rec_d["index"], 0)] == 2) & ((rec_d["dir"] * rec_d["normal"]).sum(1) > 0)
+            print("  dielectric exits: %d rays, %d leave an ior >= 5 sphere, %d of them refract" %
+                  (len(do), int(ex.sum()), int((ex & (np.abs((rec_d["scat_dir"] * rec_d["normal"]).sum(1)) > 0) &
+                                                 ((rec_d["scat_dir"] * rec_d["normal"]).sum(1) > 0)).sum())))
         np.savez_compressed(os.path.join(GOLD, "rays_%s.npz" % name), **out)
         print(name, "segments", len(rec["t"]), "hits", int((rec["index"] >= 0).sum()), "edge rays", len(et),
               "edge hits", int((ei >= 0).sum()))
@@ -130,6 +165,14 @@ def main():
                                                                           stats["render"][name]["rays_per_sample"], el))
         ref.scene_destroy(s)
 
+    if "synth4096" in args.scenes.split(","):
+        # no executable holds the 4096-sphere scene: rays per sample at 1280x720 from the patched library (16 spp = 14.7 M samples)
+        s = ref4096.scene_create("synth4096")
+        _, rays, el = ref4096.render(s, 1280, 720, 16)
+        ref4096.scene_destroy(s)
+        stats.setdefault("default_workload", {})["synth4096"] = dict(w=1280, h=720, spp=16, num_rays=[rays], rays_per_sample=rays / (1280 * 720 * 16),
+                                                                     note="patched library render at 16 spp (rays per sample does not depend on spp)")
+        print("synth4096 1280x720x16: %.4f rays/sample, %.2f Mrays/s here" % (rays / (1280 * 720 * 16), rays / el / 1e6))
     if not args.skip_exe:
         # the unmodified executable at its compiled-in workload (1280x720x250, common.h:19-25), three runs
         with tempfile.TemporaryDirectory() as tmp:
@@ -142,9 +185,9 @@ def main():
             m = re.match(r"total rays:\s+(\d+)", line)
             if m and cur:
                 runs.setdefault(cur, []).append(int(m.group(1)))
-        stats["default_workload"] = {k: dict(w=1280, h=720, spp=250, num_rays=v,
-                                             rays_per_sample=float(np.mean(v)) / (1280 * 720 * 250))
-                                     for k, v in runs.items()}
+        stats.setdefault("default_workload", {}).update({k: dict(w=1280, h=720, spp=250, num_rays=v,
+                                                                 rays_per_sample=float(np.mean(v)) / (1280 * 720 * 250))
+                                                         for k, v in runs.items()})
         print(stats["default_workload"])
     json.dump(stats, open(stats_path, "w"), indent=1, sort_keys=True)
 

@@ -77,8 +77,45 @@ static inline v3 v3_mul(v3 a, v3 b) { return v3_make(a.x * b.x, a.y * b.y, a.z *
 static inline v3 v3_scale(v3 a, float s) { return v3_make(a.x * s, a.y * s, a.z * s); }
 /* mymath.h:203-204 -- dot = sum(a*b) = (x + y) + z */
 static inline float v3_dot(v3 a, v3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
-/* mymath.h:206-208 */
-static inline v3 v3_unit(v3 v) { return v3_scale(v, 1.0f / sqrtf(v3_dot(v, v))); }
+/* mymath.h:206-208 -- unit_vector = v * (1 / length(v)).  Built with -ffast-math (bench.py:175) this is vrsqrtss + ONE Newton
+ * step, in this order (disassembly of the Ray ctor inlined into scatter() / getRay()):
+ *     y = rsqrtss(x) ; a = y * x ; a = fma(a, y, -3) ; b = y * -0.5 ; inv = a * b ; v * inv
+ * RSQRTSS is a 2048-case table on Intel CPUs (rays1bench_b200/csrc/r1_rsqrt12_table.h, measured by tools/gen_rsqrt12_table.c),
+ * restated here so that the oracle gives the same bits on any host.  The step's result is always slightly below 1/sqrt(x)
+ * (-1.5 eps^2): directions come out up to 1.6e-7 SHORT of unit length, which is visible in the statistics of large scenes
+ * (far hit points land inside their spheres and self-hit).  g_as_built = 0 keeps the exact 1 / sqrtf. */
+#include "../rays1bench_b200/csrc/r1_rsqrt12_table.h"
+static const uint16_t k_rsqrt12[R1_RSQRT12_ENTRIES] = R1_RSQRT12_INIT;
+static int g_as_built;
+static inline float rsqrt12(float x)
+{
+    uint32_t xb, yb;
+    memcpy(&xb, &x, 4);
+    if (xb < 0x00800000u) return INFINITY;                                  /* zero / denormal (and negative: not used) */
+    yb = 0x3e800000u + ((uint32_t)k_rsqrt12[(xb >> 13) & 0x7ff] << 11) - ((((xb >> 23) - 127u) & ~1u) << 22);
+    float y;
+    memcpy(&y, &yb, 4);
+    return y;
+}
+static inline float inv_length_as_built(float x)
+{
+    const float y = rsqrt12(x);
+    const float a = fmaf(y * x, y, -3.0f), b = y * -0.5f;
+    return a * b;
+}
+static inline v3 v3_unit(v3 v)
+{
+    const float x = v3_dot(v, v);
+    return v3_scale(v, g_as_built ? inv_length_as_built(x) : 1.0f / sqrtf(x));
+}
+/* the CPU's own RSQRTSS, for the test that pins the table against real hardware (x86 only) */
+#if defined(__SSE__)
+#include <xmmintrin.h>
+ORC_API float orc_hw_rsqrtss(float x) { return _mm_cvtss_f32(_mm_rsqrt_ss(_mm_set_ss(x))); }
+#else
+ORC_API float orc_hw_rsqrtss(float x) { return rsqrt12(x); }
+#endif
+ORC_API float orc_rsqrt12(float x) { return rsqrt12(x); }
 /* mymath.h:188-195 */
 static inline v3 v3_cross(v3 a, v3 b)
 {
@@ -235,17 +272,20 @@ static void build_grid(orc_scene *s, float aspect, int gw, int gh, int ior_mod, 
     for (int y = 0; y < H; ++y) {
         for (int x = 0; x < W; ++x) {
             v3 pos = v3_make((x - W / 2) * 1.1f, 0, (y - H / 2) * 1.1f);
-            float r = (rand() & 0xff) / 255.0f;
-            float g = (rand() & 0xff) / 255.0f;
-            float b = (rand() & 0xff) / 255.0f;
+            /* :679-681, :692, :696 as the fast-math build evaluates them (checked bit for bit against the recorded SoA):
+             * x / 255.0f -> x * (1 / 255.0f);  1.2f + i * 0.05f -> fma;  0.01f + 0.5f * y / H -> fma(0.5f * y, 1 / H, 0.01f) */
+            float r = g_as_built ? (rand() & 0xff) * (1.0f / 255.0f) : (rand() & 0xff) / 255.0f;
+            float g = g_as_built ? (rand() & 0xff) * (1.0f / 255.0f) : (rand() & 0xff) / 255.0f;
+            float b = g_as_built ? (rand() & 0xff) * (1.0f / 255.0f) : (rand() & 0xff) / 255.0f;
             int i = x + y * W;
             float radius = 0.45f;
             if (i % 20 == 0) {
                 int k = ior_mod ? (i % ior_mod) : i;
-                add_dielectric(s, pos, radius, 1.2f + k * 0.05f);
+                add_dielectric(s, pos, radius, g_as_built ? fmaf((float)k, 0.05f, 1.2f) : 1.2f + k * 0.05f);
             } else if (i % 10 == 0) {
                 pos = v3_add(pos, v3_make(0, 0.1f, 0));
-                add_metal(s, pos, radius, v3_make(r, g, b), 0.01f + 0.5f * y / (float)(H));
+                add_metal(s, pos, radius, v3_make(r, g, b),
+                          g_as_built ? fmaf(0.5f * y, 1.0f / (float)(H), 0.01f) : 0.01f + 0.5f * y / (float)(H));
             } else {
                 add_lambert(s, pos, radius, v3_make(r, g, b));
             }
@@ -297,13 +337,21 @@ ORC_API void orc_scene_get_camera(const orc_scene *s, float *out)
     out[21] = s->lens_radius;
 }
 
+/* Installs the 22 camera constants as given (order of orc_scene_get_camera).  The reference's Camera::init is folded at
+ * compile time by gcc -ffast-math and differs from a run-time evaluation of rayweek1.cpp:366-379 by up to 4 ulp; fixtures
+ * that need bit-identical primary rays (per-pixel replay) install the recorded constants. */
+ORC_API void orc_scene_set_camera(orc_scene *s, const float *cam)
+{
+    v3 *dst[7] = { &s->origin, &s->llc, &s->horizontal, &s->vertical, &s->u, &s->v, &s->w };
+    for (int k = 0; k < 7; ++k) *dst[k] = v3_make(cam[3 * k], cam[3 * k + 1], cam[3 * k + 2]);
+    s->lens_radius = cam[21];
+}
+
 /* ------------------------------------------------------------------ hit (rayweek1.cpp:152-339) */
 
 typedef struct { float t; v3 p, normal; int32_t index; } hit_rec;
 
 /* 1: arithmetic association of the reference AS BUILT by bench.py:175 (gcc -ffast-math); 0: as written in the source. */
-static int g_as_built = 1;
-ORC_API void orc_set_as_built(int v) { g_as_built = v; }
 
 static int scene_hit(const orc_scene *s, v3 o, v3 d, float t_min, float t_max, hit_rec *rec)
 {
@@ -366,8 +414,31 @@ ORC_API void orc_hit(const orc_scene *s, int n, const float *org, const float *d
 
 /* ------------------------------------------------------------------ scatter (rayweek1.cpp:396-512) */
 
+/* g_as_built (hit(), above) also selects the association the reference's BINARY uses in scatter().  Read from the
+ * disassembly of oracle/_ref/libref_rays1.so (gcc 13.3, bench.py:175 flags; Lambertian/Metal/Dielectric::scatter):
+ *   - every dot() is mul, mul, mul, add, add -- (x + y) + z, never contracted (mymath.h:203-204);
+ *   - reflect (:414-417) is one fnmadd per component: v - (2 dn) n with 2 dn = dn + dn;
+ *   - Metal's  reflected + fuzz * rs  (:430) is one fma per component;
+ *   - refract (:439-452): w = fma(dt, dt, -1); m = (k k) w; taken iff m > -1; discriminant = m + 1;
+ *     refracted = fnmadd(n', sqrt(discriminant), k * fnmadd(dt, n', uv));
+ *   - schlick (:454-459): r0s = (1 - ior) / (ior + 1); powf(x, 5) expanded by -ffast-math into ((x x)(x x)) * ((1 - r0) x)
+ *     with 1 - r0 = fnmadd(r0s, r0s, 1) and the sum as fma(r0s, r0s, .);
+ *   - the Ray ctor's normalise (:104-108, mymath.h:206-208) is vrsqrtss + one Newton step (hardware-specific table, <= 2e-7
+ *     from the exact value); restated here as 1 / sqrtf.
+ * The source order (g_as_built = 0) differs from the binary by up to 7.6e-6 on the golden rays (k^2 = ior^2 up to 585
+ * amplifies the rounding of 1 - dt^2); the as-built order by the normalise only (~2e-7). */
+static int g_as_built = 1;
+ORC_API void orc_set_as_built(int v) { g_as_built = v; }
+
 /* :414-417 */
-static inline v3 reflect(v3 v, v3 n) { return v3_sub(v, v3_scale(n, 2 * v3_dot(v, n))); }
+static inline v3 reflect(v3 v, v3 n)
+{
+    if (g_as_built) {
+        const float dn = v3_dot(v, n), k = dn + dn;
+        return v3_make(fmaf(-n.x, k, v.x), fmaf(-n.y, k, v.y), fmaf(-n.z, k, v.z));
+    }
+    return v3_sub(v, v3_scale(n, 2 * v3_dot(v, n)));
+}
 
 /* :439-452 */
 static inline int refract(v3 uv, v3 n, float ni_over_nt, v3 *refracted)
@@ -410,13 +481,34 @@ static int scatter_explicit(const orc_scene *s, int idx, v3 dir_in, v3 p, v3 nor
     }
     case ORC_MAT_METAL: { /* :427-433 */
         v3 reflected = reflect(dir_in, normal);
-        *dir_out = v3_unit(v3_add(reflected, v3_scale(rs, s->param[idx])));
+        const float fuzz = s->param[idx];
+        if (g_as_built) *dir_out = v3_unit(v3_make(fmaf(fuzz, rs.x, reflected.x), fmaf(fuzz, rs.y, reflected.y), fmaf(fuzz, rs.z, reflected.z)));
+        else *dir_out = v3_unit(v3_add(reflected, v3_scale(rs, fuzz)));
         *atten = v3_make(al[0], al[1], al[2]);
         return v3_dot(*dir_out, normal) > 0;
     }
     case ORC_MAT_DIELECTRIC: { /* :470-511 */
         const float ref_idx = s->param[idx];
         *atten = v3_make(1, 1, 1);
+        if (g_as_built) { /* the binary's association, see the notes above reflect() */
+            const float dn = v3_dot(dir_in, normal);
+            v3 n1;
+            float k, cosine, dt;
+            if (dn > 0) { n1 = v3_make(-normal.x, -normal.y, -normal.z); k = ref_idx; cosine = dn * ref_idx; dt = v3_dot(n1, dir_in); }
+            else { n1 = normal; k = 1.0f / ref_idx; cosine = -dn; dt = dn; }
+            const float m = (k * k) * fmaf(dt, dt, -1.0f);
+            float prob = 1.0f;
+            v3 refr = v3_make(0, 0, 0);
+            if (m > -1.0f) {
+                const float sq = sqrtf(m + 1.0f);
+                const v3 a = v3_make(fmaf(-dt, n1.x, dir_in.x), fmaf(-dt, n1.y, dir_in.y), fmaf(-dt, n1.z, dir_in.z));
+                refr = v3_make(fmaf(-n1.x, sq, k * a.x), fmaf(-n1.y, sq, k * a.y), fmaf(-n1.z, sq, k * a.z));
+                const float r0s = (1.0f - ref_idx) / (ref_idx + 1.0f), x = 1.0f - cosine;
+                prob = fmaf(r0s, r0s, ((x * x) * (x * x)) * (fmaf(-r0s, r0s, 1.0f) * x));
+            }
+            *dir_out = v3_unit(ru < prob ? reflect(dir_in, normal) : refr);
+            return 1;
+        }
         v3 outward_normal, refracted = v3_make(0, 0, 0);
         v3 reflected = reflect(dir_in, normal);
         float ni_over_nt, reflect_prob, cosine;
@@ -460,6 +552,16 @@ ORC_API void orc_scatter(const orc_scene *s, int n, const float *dir_in, const f
 static inline void camera_ray(const orc_scene *s, float su, float tv, float disk_x, float disk_y, v3 *org, v3 *dir)
 {
     float rdx = s->lens_radius * disk_x, rdy = s->lens_radius * disk_y;
+    if (g_as_built) {
+        /* the binary: offset = fma(v, rd.y, u * rd.x) ; dir = ((llc - origin) + fma(t, vertical, s * horizontal)) - offset */
+        v3 offset = v3_make(fmaf(s->v.x, rdy, s->u.x * rdx), fmaf(s->v.y, rdy, s->u.y * rdx), fmaf(s->v.z, rdy, s->u.z * rdx));
+        *org = v3_add(s->origin, offset);
+        v3 lo = v3_sub(s->llc, s->origin);
+        v3 sv = v3_make(fmaf(tv, s->vertical.x, su * s->horizontal.x), fmaf(tv, s->vertical.y, su * s->horizontal.y),
+                        fmaf(tv, s->vertical.z, su * s->horizontal.z));
+        *dir = v3_unit(v3_sub(v3_add(lo, sv), offset));
+        return;
+    }
     v3 offset = v3_add(v3_scale(s->u, rdx), v3_scale(s->v, rdy));
     *org = v3_add(s->origin, offset);
     v3 d = v3_sub(v3_sub(v3_add(v3_add(s->llc, v3_scale(s->horizontal, su)), v3_scale(s->vertical, tv)), s->origin), offset);
@@ -520,7 +622,12 @@ static v3 color(v3 o, v3 d, thread_data *td)
         }
         /* :532-534 */
         float t = 0.5f * (d.y + 1.0f);
-        leaf = v3_add(v3_scale(v3_make(1.0f, 1.0f, 1.0f), 1 - t), v3_scale(v3_make(0.5f, 0.7f, 1.0f), t));
+        if (g_as_built) {   /* the binary: it = 1 - t ; fma(t, (0.5, 0.7, 1.0), it) per component */
+            const float it = 1.0f - t;
+            leaf = v3_make(fmaf(t, 0.5f, it), fmaf(t, 0.7f, it), fmaf(t, 1.0f, it));
+        } else {
+            leaf = v3_add(v3_scale(v3_make(1.0f, 1.0f, 1.0f), 1 - t), v3_scale(v3_make(0.5f, 0.7f, 1.0f), t));
+        }
         break;
     }
     while (depth > 0) leaf = v3_mul(stack[--depth], leaf);
@@ -645,6 +752,40 @@ ORC_API void orc_replay_pixels(const orc_scene *s, int n, const int32_t *xy, int
         color_sum[3 * k] = col.x; color_sum[3 * k + 1] = col.y; color_sum[3 * k + 2] = col.z;
         rays_out[k] = (uint32_t)td.num_rays;
     }
+}
+
+/* Debug aid, counterpart of ref_trace_sample (oracle/ref_harness.cpp): one sample of one pixel, segment by segment. */
+ORC_API int orc_trace_sample(const orc_scene *s, int x, int y, int image_w, int image_h, uint32_t state, const uint32_t *state4, int max_segments,
+                             float *org, float *dir, int32_t *index, float *t, int32_t *scat_ok)
+{
+    thread_data td;
+    memset(&td, 0, sizeof(td));
+    td.scene = s; td.max_bounces = 50; td.state = state;
+    memcpy(td.state4, state4, 16);
+    float xi[4], dx, dy;
+    myrand01_x4(td.state4, xi);
+    float u = (xi[0] + (float)x) * (1.0f / image_w), v = (xi[1] + (float)y) * (1.0f / image_h);
+    random_in_unit_disk(&td.state, &dx, &dy);
+    v3 o, d;
+    camera_ray(s, u, v, dx, dy, &o, &d);
+    int n = 0;
+    for (int depth = 0; n < max_segments; ++depth) {
+        org[3 * n] = o.x; org[3 * n + 1] = o.y; org[3 * n + 2] = o.z; dir[3 * n] = d.x; dir[3 * n + 1] = d.y; dir[3 * n + 2] = d.z;
+        hit_rec rec;
+        int hit = scene_hit(s, o, d, 0.001f, FLT_MAX, &rec);
+        index[n] = hit ? rec.index : -1; t[n] = hit ? rec.t : 0.0f; scat_ok[n] = 0;
+        if (!hit || depth >= 50) { ++n; break; }
+        v3 rs = v3_make(0, 0, 0), atten, nd;
+        float ru = 0;
+        int kind = s->kind[rec.index];
+        if (kind == ORC_MAT_LAMBERT || kind == ORC_MAT_METAL) rs = random_in_unit_sphere(td.state4);
+        if (kind == ORC_MAT_DIELECTRIC) ru = myrand01(&td.state);
+        int ok = scatter_explicit(s, rec.index, d, rec.p, rec.normal, rs, ru, &atten, &nd);
+        scat_ok[n] = ok; ++n;
+        if (!ok) break;
+        o = rec.p; d = nd;
+    }
+    return n;
 }
 
 /* ------------------------------------------------------------------ RNG known-answer entry points */

@@ -21,12 +21,63 @@ struct ref_scene {
     Scene *scene;
 };
 
+#ifdef REF_SYNTH4096
+// SURVEY.md 8d config 5, built with the reference's OWN classes (Scene, Hitable, SphereSOA::add, Camera::init, the three
+// materials): a 66 x 62 grid + the ground sphere + three radius-2 spheres = 4096 spheres, the recipe of create_large_scene()
+// (rayweek1.cpp:668-712) with ior = 1.2 + 0.05 (i % 480) so that it stays inside the reference's own range.  Only the build
+// whose Hitable::hit holds 4096 spheres (oracle/Makefile: MAX_SPHERES patched in a temporary copy of rayweek1.cpp:174)
+// can trace it.  The product's builder for the same scene is rays1_host.cpp:grid_scene(66, 62, 480, ...).
+static Scene *harness_synth4096_scene()
+{
+    Scene *scene = new Scene;
+    Hitable *world = new Hitable;
+    scene->hitables = world;
+    scene->camera.init(Vec3(6, 16, 30), Vec3(0, 0, 0), Vec3(0, 1, 0), 60, (float)SCREEN_W / (float)SCREEN_H, 0.1f, 20.0f);
+    const int W = 66, H = 62;
+    world->_soa_spheres.reserve(W * H + 4 + SIMD_WIDTH);
+    srand(111);
+    for (int y = 0; y < H; ++y) {
+        for (int x = 0; x < W; ++x) {
+            Vec3 pos((x - W / 2) * 1.1f, 0, (y - H / 2) * 1.1f);
+            const float r = (rand() & 0xff) / 255.0f;
+            const float g = (rand() & 0xff) / 255.0f;
+            const float b = (rand() & 0xff) / 255.0f;
+            const int i = x + y * W;
+            Material *m;
+            if (i % 20 == 0) m = new Dielectric(1.2f + (i % 480) * 0.05f);
+            else if (i % 10 == 0) { m = new Metal(Vec3(r, g, b), 0.01f + 0.5f * y / (float)(H)); pos += Vec3(0, 0.1f, 0); }
+            else m = new Lambertian(Vec3(r, g, b));
+            world->_soa_spheres.add(pos, 0.45f, m);
+        }
+    }
+    world->_soa_spheres.add(Vec3(0, -1000.5f, 0), 1000, new Lambertian(Vec3(0.5f, 0.5f, 0.5f)));
+    world->_soa_spheres.add(Vec3(5, 3, 0), 2, new Metal(Vec3(0.5f, 0.5f, 0.8f), 0.65f));
+    world->_soa_spheres.add(Vec3(0, 3, 0), 2, new Dielectric(1.5f));
+    world->_soa_spheres.add(Vec3(-5, 3, 0), 2, new Metal(Vec3(0.8f, 0.2f, 0.2f), 0.05f));
+    while (world->_soa_spheres.getCount() % SIMD_WIDTH != 0) world->_soa_spheres.add(Vec3(999999999, 999999999, 999999999), 0, nullptr);
+    return scene;
+}
+#endif
+
+// largest sphere count Hitable::hit of THIS build can hold (rayweek1.cpp:174)
+REF_API int ref_max_spheres(void)
+{
+#ifdef REF_SYNTH4096
+    return 4096;
+#else
+    return 1024;
+#endif
+}
+
 REF_API ref_scene *ref_scene_create(const char *name)
 {
     Scene *s = nullptr;
     if (!strcmp(name, "small")) s = create_small_scene();
     else if (!strcmp(name, "medium")) s = create_medium_scene();
     else if (!strcmp(name, "large")) s = create_large_scene();
+#ifdef REF_SYNTH4096
+    else if (!strcmp(name, "synth4096")) s = harness_synth4096_scene();
+#endif
     if (!s) return nullptr;
     return new ref_scene{ s };
 }
@@ -155,6 +206,77 @@ REF_API int ref_record_paths(const ref_scene *h, int max_segments, int image_w, 
             if (!ok) break;
             r = scattered;
         }
+    }
+    return n;
+}
+
+// Hitable::hit followed by Material::scatter for GIVEN rays (one segment each, unit directions): the same record as
+// ref_record_paths, for cases real camera paths reach rarely -- e.g. rays leaving the high-index dielectric spheres of the
+// large scene from inside (ior up to 24.2, rayweek1.cpp:692).  The random inputs scatter() consumed are recovered by
+// replaying the generators on copies of their states.
+REF_API void ref_hit_scatter(const ref_scene *h, int n, const float *org, const float *dir, uint32_t seed, int32_t *index, float *t, float *p,
+                             float *normal, float *rand_sphere, float *rand_u, int32_t *scat_ok, float *atten, float *scat_dir)
+{
+    ThreadData td;
+    memset(&td, 0, sizeof(td));
+    td.scene = h->scene;
+    td.state = seed * 2u + 10001u;
+    td.state4 = _mm_set_epi32(seed + 1001, seed + 1003, seed + 1005, seed + 1007);
+    for (int k = 0; k < n; ++k) {
+        Ray r;
+        r._origin = Vec3(org[3 * k], org[3 * k + 1], org[3 * k + 2]);
+        r._dir = Vec3(dir[3 * k], dir[3 * k + 1], dir[3 * k + 2]);
+        HitRecord rec;
+        memset(&rec, 0, sizeof(rec));
+        const bool hit = h->scene->hitables->hit(r, 0.001f, FLT_MAX, &rec);
+        index[k] = hit ? material_index(h, rec.material) : -1;
+        t[k] = hit ? rec.t : 0.0f;
+        for (int c = 0; c < 3; ++c) p[3 * k + c] = normal[3 * k + c] = rand_sphere[3 * k + c] = atten[3 * k + c] = scat_dir[3 * k + c] = 0;
+        rand_u[k] = 0; scat_ok[k] = 0;
+        if (!hit) continue;
+        put3(p + 3 * k, rec.p); put3(normal + 3 * k, rec.normal);
+        __m128i s4 = td.state4;
+        put3(rand_sphere + 3 * k, random_in_unit_sphere(s4));
+        uint32_t s1 = td.state;
+        rand_u[k] = myrand01(s1);
+        Vec3 attenuation(0, 0, 0);
+        Ray scattered;
+        scattered._origin = Vec3(0, 0, 0); scattered._dir = Vec3(0, 0, 0);
+        const bool ok = rec.material->scatter(r, rec, &attenuation, &scattered, &td);
+        scat_ok[k] = ok ? 1 : 0;
+        put3(atten + 3 * k, attenuation); put3(scat_dir + 3 * k, scattered._dir);
+    }
+}
+
+// Debug aid: ONE sample of ONE pixel from given generator states, walked with the reference's camera / hit / scatter and
+// recorded segment by segment (same record as ref_record_paths).  Returns the number of segments (<= max_segments).
+REF_API int ref_trace_sample(const ref_scene *h, int x, int y, int image_w, int image_h, uint32_t state, const uint32_t *state4, int max_segments,
+                             float *org, float *dir, int32_t *index, float *t, int32_t *scat_ok)
+{
+    ThreadData td;
+    memset(&td, 0, sizeof(td));
+    td.scene = h->scene;
+    td.state = state;
+    td.state4 = _mm_loadu_si128((const __m128i *)state4);
+    Vec3 uv = (Vec3(myrand01_x4(td.state4)) + Vec3((float)x, (float)y, 0)) * Vec3(1.0f / image_w, 1.0f / image_h, 0);
+    Ray r = h->scene->camera.getRay(uv.getX(), uv.getY(), td.state);
+    int n = 0;
+    for (int depth = 0; n < max_segments; ++depth) {
+        put3(org + 3 * n, r._origin); put3(dir + 3 * n, r._dir);
+        HitRecord rec;
+        memset(&rec, 0, sizeof(rec));
+        bool hit = h->scene->hitables->hit(r, 0.001f, FLT_MAX, &rec);
+        index[n] = hit ? material_index(h, rec.material) : -1;
+        t[n] = hit ? rec.t : 0.0f;
+        scat_ok[n] = 0;
+        if (!hit || depth >= MAX_BOUNCES) { ++n; break; }
+        Vec3 attenuation(0, 0, 0);
+        Ray scattered;
+        bool ok = rec.material->scatter(r, rec, &attenuation, &scattered, &td);
+        scat_ok[n] = ok ? 1 : 0;
+        ++n;
+        if (!ok) break;
+        r = scattered;
     }
     return n;
 }

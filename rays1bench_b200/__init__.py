@@ -60,6 +60,7 @@ def _load():
         "r1_scene_create": (vp, [C.c_uint32]),
         "r1_scene_destroy": (None, [vp]),
         "r1_scene_set_camera": (ci, [vp, f32p, f32p, f32p, cf, cf, cf, cf]),
+        "r1_scene_set_camera_raw": (ci, [vp, f32p]),
         "r1_scene_add_sphere": (ci, [vp, cf, cf, cf, cf, ci, cf, cf, cf, cf]),
         "r1_scene_pad": (ci, [vp, C.c_uint32]),
         "r1_scene_count": (C.c_uint32, [vp]),
@@ -84,9 +85,9 @@ def _load():
         "r1_host_create_scene": (vp, [C.c_char_p, ci]),
         "r1_host_create_scene_from_file": (vp, [C.c_char_p, ci]),
         "r1_host_scene_handle": (vp, [vp]),
-        "r1_host_benchmark": (ci, [vp, u8p, ci, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
+        "r1_host_benchmark": (ci, [vp, u8p, C.c_uint64, ci, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
         "r1_host_destroy_scene": (None, [vp]),
-        "r1_host_write_tga": (ci, [C.c_char_p, ci, ci, u8p]),
+        "r1_host_write_tga": (ci, [C.c_char_p, ci, ci, u8p, C.c_uint64]),
         "r1_host_log_results": (ci, [C.c_char_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), ci]),
     }
     for name, (res, args) in sig.items():
@@ -155,6 +156,12 @@ class Scene:
         _check(lib.r1_scene_get_camera(self.handle, out), "r1_scene_get_camera")
         return out
 
+    def set_camera_raw(self, cam22, device=None):
+        """install the 22 camera constants as given (e.g. the reference's recorded ones) and re-commit the scene"""
+        _check(lib.r1_scene_set_camera_raw(self.handle, np.ascontiguousarray(cam22, np.float32)), "r1_scene_set_camera_raw")
+        if device is not None:
+            _check(lib.r1_scene_commit(self.handle, device), "r1_scene_commit")
+
     # -- device entry points
     def render(self, width=SCREEN_W, height=SCREEN_H, spp=NUM_SAMPLES_PER_PIXEL, max_bounces=MAX_BOUNCES, variant=VARIANT_MEGAKERNEL,
                seed=0, rank=0, world=1, row_tile=DEFAULT_ROW_TILE, device=-1, blocks_per_sm=0, threads=0):
@@ -222,10 +229,17 @@ class Scene:
         return org, d
 
 
+_configured = {"width": SCREEN_W, "height": SCREEN_H}
+
+
 def configure(width=0, height=0, spp=0, max_bounces=0, variant=-1, n_gpus=0, seed=0, quiet=None):
     """Runtime stand-in for the reference's compile-time macros (common.h:3-31).  Affects scenes created afterwards
     (camera aspect, GPU replicas) and benchmark()."""
     _check(lib.r1_host_configure(width, height, spp, max_bounces, variant, n_gpus, seed), "r1_host_configure")
+    if width > 0:
+        _configured["width"] = width
+    if height > 0:
+        _configured["height"] = height
     if quiet is not None:
         lib.r1_host_set_quiet(1 if quiet else 0)
 
@@ -282,12 +296,16 @@ def benchmark(scene, pixels, write_tga, scene_name):
     out_<scene_name>.tga (which swaps R and B in ``pixels`` in place).  Returns a Result (elapsed_seconds, num_rays)."""
     if pixels.dtype != np.uint8 or not pixels.flags["C_CONTIGUOUS"]:
         raise ValueError("pixels must be a C-contiguous uint8 array")
+    need = _configured["width"] * _configured["height"] * 3
+    if pixels.size != need:
+        raise ValueError("pixels has %d bytes, the configured %dx%d image needs %d (call configure() first)" %
+                         (pixels.size, _configured["width"], _configured["height"], need))
     el, rays, kms = C.c_double(0), C.c_uint64(0), C.c_double(0)
     ptr, scene._ptr = scene._ptr, None  # ownership moves to benchmark() (delete scene, rayweek1.cpp:905)
     if not ptr:
         raise Rays1Error("scene %r was already consumed" % scene.name)
-    _check(lib.r1_host_benchmark(ptr, pixels.reshape(-1), 1 if write_tga else 0, scene_name.encode(), C.byref(el), C.byref(rays), C.byref(kms)),
-           "benchmark")
+    _check(lib.r1_host_benchmark(ptr, pixels.reshape(-1), pixels.size, 1 if write_tga else 0, scene_name.encode(), C.byref(el), C.byref(rays),
+                                 C.byref(kms)), "benchmark")
     res = Result()
     res.elapsed_seconds, res.num_rays, res.kernel_ms = el.value, rays.value, kms.value
     return res
@@ -295,7 +313,9 @@ def benchmark(scene, pixels, write_tga, scene_name):
 
 def tga_write_rgb24(filename, width, height, pixels):
     """tga_write_rgb24 (common.h:86-122).  !!! swaps R and B in ``pixels`` in place, like the reference."""
-    _check(lib.r1_host_write_tga(filename.encode(), width, height, pixels.reshape(-1)), "tga_write_rgb24")
+    if pixels.dtype != np.uint8 or not pixels.flags["C_CONTIGUOUS"] or pixels.size < width * height * 3:
+        raise ValueError("pixels must be a C-contiguous uint8 array of at least width * height * 3 bytes")
+    _check(lib.r1_host_write_tga(filename.encode(), width, height, pixels.reshape(-1), pixels.size), "tga_write_rgb24")
 
 
 def log_results(version, scene, results):

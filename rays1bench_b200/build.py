@@ -3,7 +3,8 @@
   rays1bench_b200/librays1_b200.so   C-ABI library: CUDA kernels + reference-shaped host layer (include/rays1_b200.h)
   rays1bench_b200/rays1_b200         drop-in executable (`[-w] [-n N]`, src/latest/rayweek1.cpp:930-988 of the reference)
 
-nvcc cross-compiles without a GPU.  `python -m rays1bench_b200.build` or `build()` from __graft_entry__.
+nvcc cross-compiles without a GPU.  `python rays1bench_b200/build.py [--force] [-v]` (run by path: importing the package
+needs the library this script builds) or `build()` from __graft_entry__, which always recompiles.
 """
 import os
 import shutil

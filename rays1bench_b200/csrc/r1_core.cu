@@ -3,6 +3,7 @@
 // returns R1_ERR_CUDA if the CUDA runtime reports an error (including "no device").
 // file:line citations are relative to /root/reference/.
 #include "../../include/rays1_b200.h"
+#include "r1_internal.h"
 #include "r1_kernels.cuh"
 #include "r1_wavefront.cuh"
 
@@ -22,16 +23,7 @@ namespace {
 
 thread_local std::string g_error;
 
-int fail(int code, const char *fmt, ...)
-{
-    char buf[512];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof(buf), fmt, ap);
-    va_end(ap);
-    g_error = buf;
-    return code;
-}
+#define fail r1_set_error
 
 #define R1_CUDA(expr)                                                                                        \
     do {                                                                                                     \
@@ -68,6 +60,17 @@ std::mutex g_scratch_mutex;
 std::map<int, Scratch> g_scratch;
 
 }  // namespace
+
+int r1_set_error(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
 
 struct r1_scene {
     // SphereSOA (soa_sphere.h:38-53) with the Material hierarchy flattened to (kind, albedo, param)
@@ -164,7 +167,7 @@ int launch_megakernel_t(int sm_count, const r1::RenderArgs &args, const r1_rende
 {
     constexpr int kBlocks = 1;
     auto kern = r1::megakernel<kScan, kStaged, kThreads, kBlocks>;
-    const size_t smem = 16 + (kStaged ? (size_t)args.scene.n_pad * 32 : 0) + (kScan == r1::kScanCoop ? sizeof(r1::WarpScratch) * (kThreads / 32) : 0);
+    const size_t smem = r1::kSmemSpheres + (kStaged ? (size_t)args.scene.n_pad * 32 : 0) + (kScan == r1::kScanCoop ? sizeof(r1::WarpScratch) * (kThreads / 32) : 0);
     R1_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = sm_count * kBlocks;
     if (prm.blocks_per_sm > 0) grid = sm_count * prm.blocks_per_sm;
@@ -192,6 +195,9 @@ int validate(const r1_render_params *p)
     if (p->width <= 0 || p->height <= 0 || p->spp <= 0 || p->max_bounces < 0) return fail(R1_ERR_ARG, "width/height/spp must be > 0, max_bounces >= 0");
     if (p->world <= 0 || p->rank < 0 || p->rank >= p->world) return fail(R1_ERR_ARG, "bad rank/world %d/%d", p->rank, p->world);
     if ((uint64_t)p->width * (uint64_t)p->height > (1ull << 31)) return fail(R1_ERR_ARG, "image too large");
+    // the pixel accumulators hold sums of radiance * 2^40 in 64 bits with samples clamped to 4.0 (r1_kernels.cuh): 2^22 samples
+    // would wrap; 2^20 is the documented limit
+    if (p->spp > (1 << 20)) return fail(R1_ERR_LIMIT, "spp %d exceeds the accumulator limit of 2^20 samples per pixel", p->spp);
     if (p->variant < 0 || p->variant > 3) return fail(R1_ERR_ARG, "unknown variant %d", p->variant);
     return R1_OK;
 }
@@ -251,6 +257,17 @@ int r1_scene_set_camera(r1_scene *scene, const float lookfrom[3], const float lo
         c.horizontal[k] = (2 * half_width * focus_dist) * c.u[k];
         c.vertical[k] = (2 * half_height * focus_dist) * c.v[k];
     }
+    scene->have_camera = true;
+    return R1_OK;
+}
+
+int r1_scene_set_camera_raw(r1_scene *scene, const float cam[22])
+{
+    if (!scene || !cam) return fail(R1_ERR_ARG, "null argument");
+    r1::Camera &c = scene->cam;
+    float *dst[7] = { c.origin, c.llc, c.horizontal, c.vertical, c.u, c.v, c.w };
+    for (int k = 0; k < 7; ++k) memcpy(dst[k], cam + 3 * k, 12);
+    c.lens_radius = cam[21];
     scene->have_camera = true;
     return R1_OK;
 }

@@ -26,12 +26,13 @@ struct RenderArgs {
     int32_t rank, world, row_tile;
     uint32_t npix_local, n_units;
     int32_t samples_per_unit, n_chunks;
-    uint32_t seed;                   // Rng::seed_hash(global seed)
     float inv_w, inv_h, inv_spp;
+    uint64_t seed;                   // Rng::seed_hash(global seed)
     uint64_t magic_chunks, magic_width, magic_row_tile;  // floor(2^64 / d) + 1: exact n / d for 32-bit n via one 64-bit mul-high (0 when d == 1)
     uint32_t sched_kmax, sched_div;      // unit ranges: a lane takes min(kmax, max(1, units_left / (lanes * div))) units per fetch
 };
 
+constexpr int kSmemSpheres = 16 + R1_RSQRT12_ENTRIES * 2;   // megakernel: byte offset of the staged spheres (mbarrier, rsqrtss table first)
 constexpr float kFixedScale = 1099511627776.0f;            // 2^40
 constexpr float kFixedInvScale = 9.094947017729282e-13f;   // 2^-40
 
@@ -102,18 +103,20 @@ __device__ __forceinline__ void accumulate_sample(const RenderArgs &a, uint32_t 
 }
 
 // start sample s of a pixel: jitter (rayweek1.cpp:759), lens disk + camera ray (:760, :381-386)
-__device__ __forceinline__ void primary_ray(const RenderArgs &a, uint32_t pixel, float fx, float fy, int s, Rng &rng, f3 &o, f3 &d)
+__device__ __forceinline__ void primary_ray(const RenderArgs &a, uint32_t pixel, float fx, float fy, int s, const uint16_t *__restrict__ tab, Rng &rng, f3 &o,
+                                            f3 &d)
 {
     rng.seed(pixel, (uint32_t)s, a.seed);
-    const float u = fmul(fadd(rng.rand01(), fx), a.inv_w), v = fmul(fadd(rng.rand01(), fy), a.inv_h);
+    const float u = fmul(fadd(rng.rand01(0), fx), a.inv_w), v = fmul(fadd(rng.rand01(1), fy), a.inv_h);
     float px, py;
-    random_in_unit_disk(rng, px, py);
-    camera_ray(a.scene.cam, u, v, px, py, o, d);
+    random_in_unit_disk(rng, 2, px, py);
+    camera_ray(a.scene.cam, u, v, px, py, tab, o, d);
 }
 
 // color() body after hit() (rayweek1.cpp:515-536).  Returns true when the path ends (contrib = its radiance);
 // otherwise o / d / thr / depth hold the scattered ray.  `e` is the hit sphere's exact record.
-__device__ __forceinline__ bool shade_step(const RenderArgs &a, int hit, float t, float4 e, f3 &o, f3 &d, f3 &thr, int &depth, Rng &rng, f3 &contrib)
+__device__ __forceinline__ bool shade_step(const RenderArgs &a, int hit, float t, float4 e, const uint16_t *__restrict__ tab, f3 &o, f3 &d, f3 &thr, int &depth,
+                                           const Rng &rng, f3 &contrib)
 {
     contrib = mk3(0, 0, 0);
     if (hit < 0) {
@@ -127,9 +130,10 @@ __device__ __forceinline__ bool shade_step(const RenderArgs &a, int hit, float t
     hit_finalise(e, __ldg(a.scene.inv_radius + hit), o, d, t, p, n);
     const int kind = __ldg(a.scene.kind + hit);
     const float4 mat = __ldg(a.scene.mat + hit);
-    if (kind == 2) ru = rng.rand01();
-    else rs = random_in_unit_sphere(rng);
-    if (!scatter(kind, mat, d, p, n, rs, ru, atten, nd)) return true;
+    const uint32_t draw0 = kDrawsPrimary + kDrawsPerBounce * (uint32_t)depth;
+    if (kind == 2) ru = rng.rand01(draw0);
+    else rs = random_in_unit_sphere(rng, draw0);
+    if (!scatter(kind, mat, d, p, n, rs, ru, tab, atten, nd)) return true;
     thr = mk3(fmul(thr.x, atten.x), fmul(thr.y, atten.y), fmul(thr.z, atten.z));
     o = p; d = nd; ++depth;
     return false;
@@ -145,21 +149,27 @@ enum ScanKind { kScanCoop = 0, kScanLanePacked = 1, kScanLaneScalar = 2 };
 template <int kScan, bool kStaged, int kThreads, int kBlocksPerSM>
 __global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel(const __grid_constant__ RenderArgs a)
 {
+    // shared memory: [mbarrier 16 B | rsqrtss table 4 KB | staged spheres n_pad * 32 B | per-warp scratch (cooperative scan)]
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint16_t *s_tab = reinterpret_cast<uint16_t *>(smem_raw + 16);
+    for (int i = threadIdx.x; i < R1_RSQRT12_ENTRIES / 2; i += kThreads)
+        reinterpret_cast<uint32_t *>(s_tab)[i] = reinterpret_cast<const uint32_t *>(g_rsqrt12)[i];
     const float4 *s_scan, *s_exact;
     if (kStaged) {
-        float4 *s_spheres = reinterpret_cast<float4 *>(smem_raw + 16);
-        stage_spheres(a.scene, s_spheres, reinterpret_cast<uint64_t *>(smem_raw));
+        float4 *s_spheres = reinterpret_cast<float4 *>(smem_raw + kSmemSpheres);
+        stage_spheres(a.scene, s_spheres, reinterpret_cast<uint64_t *>(smem_raw));   // its __syncthreads also publishes the table
         s_scan = s_spheres;
         s_exact = s_spheres + a.scene.n_pad;
     } else {  // scenes beyond the staging limit scan straight from global memory (L1/L2 resident)
         s_scan = a.scene.scan;
         s_exact = a.scene.exact;
+        __syncthreads();
     }
+    const uint16_t *tab = s_tab;
     const int n_pad = a.scene.n_pad;
     const unsigned lane = threadIdx.x & 31u;
     // per-warp scratch of the cooperative scan, behind the staged spheres
-    WarpScratch *ws = reinterpret_cast<WarpScratch *>(smem_raw + 16 + (kStaged ? (size_t)n_pad * 32 : 0)) + (threadIdx.x >> 5);
+    WarpScratch *ws = reinterpret_cast<WarpScratch *>(smem_raw + kSmemSpheres + (kStaged ? (size_t)n_pad * 32 : 0)) + (threadIdx.x >> 5);
 
     bool active = false, exhausted = false, need_primary = false;
     uint32_t unit = 0, unit_end = 0, lp = 0, pixel = 0, nrays = 0, last_base = 0;
@@ -168,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel(const __gri
     f3 thr = mk3(1, 1, 1);
     f3 o = mk3(0.0f, 1.0e18f, 0.0f), d = mk3(0.0f, 0.0f, 0.0f);  // idle lanes scan a ray that passes no filter
     Rng rng;
-    rng.key = 0; rng.ctr = 0;
+    rng.k0 = 0; rng.k1 = 0;
     const uint32_t lanes_x4 = gridDim.x * blockDim.x * a.sched_div;
 
     for (;;) {
@@ -203,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel(const __gri
 
         // -- start a sample
         if (active && need_primary) {
-            primary_ray(a, pixel, fx, fy, s, rng, o, d);
+            primary_ray(a, pixel, fx, fy, s, tab, rng, o, d);
             thr = mk3(1, 1, 1);
             depth = 0;
             need_primary = false;
@@ -220,7 +230,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel(const __gri
             ++nrays;
             f3 contrib;
             const float4 e = hit >= 0 ? s_exact[hit] : make_float4(0, 0, 0, 0);
-            if (shade_step(a, hit, t, e, o, d, thr, depth, rng, contrib)) {
+            if (shade_step(a, hit, t, e, tab, o, d, thr, depth, rng, contrib)) {
                 accumulate_sample(a, lp, contrib);
                 need_primary = true;
                 if (++s == s_end) {                          // unit done: the next one of my range, or a new range
@@ -310,7 +320,7 @@ __global__ void scatter_kernel(const __grid_constant__ DevScene sc, int n, const
     bool r = false;
     if (i >= 0 && i < sc.n_pad && sc.kind[i] >= 0)
         r = scatter(sc.kind[i], sc.mat[i], mk3(dir_in[3 * k], dir_in[3 * k + 1], dir_in[3 * k + 2]), mk3(p[3 * k], p[3 * k + 1], p[3 * k + 2]),
-                    mk3(nrm[3 * k], nrm[3 * k + 1], nrm[3 * k + 2]), mk3(rs[3 * k], rs[3 * k + 1], rs[3 * k + 2]), ru[k], a, dd);
+                    mk3(nrm[3 * k], nrm[3 * k + 1], nrm[3 * k + 2]), mk3(rs[3 * k], rs[3 * k + 1], rs[3 * k + 2]), ru[k], g_rsqrt12, a, dd);
     ok[k] = r ? 1 : 0;
     atten[3 * k] = a.x; atten[3 * k + 1] = a.y; atten[3 * k + 2] = a.z;
     dir_out[3 * k] = dd.x; dir_out[3 * k + 1] = dd.y; dir_out[3 * k + 2] = dd.z;
@@ -321,7 +331,7 @@ __global__ void get_ray_kernel(const __grid_constant__ DevScene sc, int n, const
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     f3 o, d;
-    camera_ray(sc.cam, su[k], tv[k], disk[2 * k], disk[2 * k + 1], o, d);
+    camera_ray(sc.cam, su[k], tv[k], disk[2 * k], disk[2 * k + 1], g_rsqrt12, o, d);
     org[3 * k] = o.x; org[3 * k + 1] = o.y; org[3 * k + 2] = o.z;
     dir[3 * k] = d.x; dir[3 * k + 1] = d.y; dir[3 * k + 2] = d.z;
 }
@@ -331,7 +341,7 @@ __global__ void rng_kernel(uint32_t pixel, uint32_t sample, uint32_t seed, int n
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         Rng rng;
         rng.seed(pixel, sample, Rng::seed_hash(seed));
-        for (int i = 0; i < n; ++i) out[i] = rng.next();
+        for (int i = 0; i < n; ++i) out[i] = rng.draw((uint32_t)i);
     }
 }
 
@@ -382,7 +392,7 @@ __global__ void __launch_bounds__(128) replay_pixels_kernel(const __grid_constan
             px = fsub(rng.rand02(), 1.0f);
         } while (fadd(fmul(px, px), fmul(py, py)) >= 1.0f);
         f3 o, d;
-        camera_ray(sc.cam, u, v, px, py, o, d);
+        camera_ray(sc.cam, u, v, px, py, g_rsqrt12, o, d);
         f3 stack[51];
         int depth = 0;
         f3 leaf = mk3(0, 0, 0);
@@ -406,7 +416,7 @@ __global__ void __launch_bounds__(128) replay_pixels_kernel(const __grid_constan
                     rs = mk3(fsub(r4[0], 1.0f), fsub(r4[1], 1.0f), fsub(r4[2], 1.0f));
                 } while (fadd(fadd(fmul(rs.x, rs.x), fmul(rs.y, rs.y)), fmul(rs.z, rs.z)) >= 1.0f);
             }
-            if (!scatter(kind, sc.mat[hit], d, p, nrm, rs, ru, atten, nd)) break;
+            if (!scatter(kind, sc.mat[hit], d, p, nrm, rs, ru, g_rsqrt12, atten, nd)) break;
             stack[depth++] = atten;
             o = p; d = nd;
         }

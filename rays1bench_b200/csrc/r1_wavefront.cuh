@@ -26,7 +26,7 @@ constexpr uint32_t kDead = 0xffffffffu;
 
 // One 64-byte record per slot (two 32-byte sectors): intersect touches the first sector only, shade reads and writes both.
 //   [0] origin.xyz, hit t      [1] dir.xyz, hit sphere index (int bits)
-//   [2] throughput.rgb, depth (int bits)      [3] unit (kDead = slot retired), sample index, rng key, rng ctr  (uint bits)
+//   [2] throughput.rgb, depth (int bits)      [3] unit (kDead = slot retired), sample index, rng key words k0, k1  (uint bits)
 // (The first layout kept six separate SoA arrays: wf_shade, which visits slots in class-queue order, then moved six
 // scattered sectors per ray in each direction and took 90 ms per frame.)
 struct WfState {
@@ -58,7 +58,7 @@ __device__ __forceinline__ void wf_store_path(const WfState &w, uint32_t slot, f
     rec[0] = make_float4(o.x, o.y, o.z, 0.0f);
     rec[1] = make_float4(d.x, d.y, d.z, __int_as_float(-1));
     rec[2] = make_float4(thr.x, thr.y, thr.z, __int_as_float(depth));
-    rec[3] = make_float4(__uint_as_float(unit), __uint_as_float((uint32_t)s), __uint_as_float(rng.key), __uint_as_float(rng.ctr));
+    rec[3] = make_float4(__uint_as_float(unit), __uint_as_float((uint32_t)s), __uint_as_float(rng.k0), __uint_as_float(rng.k1));
 }
 __device__ __forceinline__ void wf_retire(const WfState &w, uint32_t slot)
 {
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) wf_init(const __grid_constant__ RenderArg
             uint32_t lp, pixel; float fx, fy; int s, s_end;
             unit_begin(a, slot, lp, pixel, fx, fy, s, s_end);
             Rng rng; f3 o, d;
-            primary_ray(a, pixel, fx, fy, s, rng, o, d);
+            primary_ray(a, pixel, fx, fy, s, g_rsqrt12, rng, o, d);
             wf_store_path(w, slot, o, d, mk3(1, 1, 1), 0, slot, s, rng);
             w.alive[0][slot] = slot;
         } else {
@@ -175,16 +175,16 @@ __global__ void __launch_bounds__(256) wf_shade(const __grid_constant__ RenderAr
         uint32_t slot = 0, unit = 0;
         int s = 0, depth = 0;
         f3 o = mk3(0, 0, 0), d = mk3(0, 0, 0), thr = mk3(1, 1, 1), contrib = mk3(0, 0, 0);
-        Rng rng; rng.key = 0; rng.ctr = 0;
+        Rng rng; rng.k0 = 0; rng.k1 = 0;
         if (valid) {
             slot = w.queue[(size_t)c * w.n_slots + j];
             const float4 *rec = w.slots + (size_t)slot * 4;
             const float4 ro = rec[0], rd = rec[1], th = rec[2], m = rec[3];
             o = mk3(ro.x, ro.y, ro.z); d = mk3(rd.x, rd.y, rd.z); thr = mk3(th.x, th.y, th.z); depth = __float_as_int(th.w);
-            unit = __float_as_uint(m.x); s = (int)__float_as_uint(m.y); rng.key = __float_as_uint(m.z); rng.ctr = __float_as_uint(m.w);
+            unit = __float_as_uint(m.x); s = (int)__float_as_uint(m.y); rng.k0 = __float_as_uint(m.z); rng.k1 = __float_as_uint(m.w);
             const int hit = __float_as_int(rd.w);
             const float4 e = hit >= 0 ? __ldg(a.scene.exact + hit) : make_float4(0, 0, 0, 0);
-            ended = shade_step(a, hit, ro.w, e, o, d, thr, depth, rng, contrib);
+            ended = shade_step(a, hit, ro.w, e, g_rsqrt12, o, d, thr, depth, rng, contrib);
             alive = true;
         }
         // path ended: add the sample to its pixel, then the next sample of the unit or the next unit (warp-aggregated atomic)
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(256) wf_shade(const __grid_constant__ RenderAr
         }
         if (valid) {
             if (ended && alive) {
-                primary_ray(a, pixel, fx, fy, s, rng, o, d);
+                primary_ray(a, pixel, fx, fy, s, g_rsqrt12, rng, o, d);
                 thr = mk3(1, 1, 1);
                 depth = 0;
             }

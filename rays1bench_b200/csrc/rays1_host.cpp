@@ -2,15 +2,18 @@
 // Mirrors src/latest/rayweek1.cpp:552-719, 845-927 and src/common/common.h:36-122 of the reference; the trace loop
 // itself runs on the GPU(s) behind r1_render / r1_render_device.  file:line citations are relative to /root/reference/.
 #include "rays1_host.h"
+#include "r1_internal.h"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
 
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 
 HostConfig &host_config()
@@ -79,18 +82,20 @@ Scene *grid_scene(int gw, int gh, int ior_mod, float fx, float fy, float fz, flo
     for (int y = 0; y < H; ++y) {
         for (int x = 0; x < W; ++x) {
             float px = (x - W / 2) * 1.1f, py = 0, pz = (y - H / 2) * 1.1f;
-            // CRT random
-            const float r = (rand() & 0xff) / 255.0f;
-            const float g = (rand() & 0xff) / 255.0f;
-            const float bl = (rand() & 0xff) / 255.0f;
+            // CRT random.  The three constant expressions below (:679-681, :692, :696) are written the way the reference's
+            // fast-math build (bench.py:175) evaluates them, so that albedo / ior / fuzz have the reference's exact bits:
+            // x / 255.0f -> x * (1 / 255.0f);  1.2f + i * 0.05f -> one fma;  0.01f + 0.5f * y / H -> fma(0.5f * y, 1 / H, 0.01f)
+            const float r = (rand() & 0xff) * (1.0f / 255.0f);
+            const float g = (rand() & 0xff) * (1.0f / 255.0f);
+            const float bl = (rand() & 0xff) * (1.0f / 255.0f);
             const int i = x + y * W;
             const float radius = 0.45f;
             if (i % 20 == 0) {
                 const int k = ior_mod ? i % ior_mod : i;
-                b.dielectric(px, py, pz, radius, 1.2f + k * 0.05f);
+                b.dielectric(px, py, pz, radius, fmaf((float)k, 0.05f, 1.2f));
             } else if (i % 10 == 0) {
                 py += 0.1f;
-                b.metal(px, py, pz, radius, r, g, bl, 0.01f + 0.5f * y / (float)(H));
+                b.metal(px, py, pz, radius, r, g, bl, fmaf(0.5f * y, 1.0f / (float)(H), 0.01f));
             } else {
                 b.lambert(px, py, pz, radius, r, g, bl);
             }
@@ -214,6 +219,9 @@ Scene *create_scene_from_file(const char *path) { return build_from_file(path); 
 // exactly two NCCL collectives over NVLink: a framebuffer gather to device 0 (grouped ncclSend/ncclRecv) and an
 // ncclReduce of the ray counters.  NCCL is dlopen'ed so that librays1_b200.so carries no link-time NCCL dependency
 // (a Python process that already loaded torch's bundled libnccl.so.2 keeps using that one).
+// Everything here RETURNS an error code (message via r1_last_error()): the C-linkage entry points hand it to their
+// caller, only the reference-shaped C++ benchmark() / create_*_scene() turn it into the fatal exit the reference's
+// no-error-path surface implies.
 namespace {
 
 struct Nccl {
@@ -226,19 +234,24 @@ struct Nccl {
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
-    bool load()
+    int load()
     {
-        if (lib) return true;
-        lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-        if (!lib) return false;
-#define R1_SYM(field, name) field = reinterpret_cast<decltype(field)>(dlsym(lib, name)); if (!field) return false;
+        if (lib) return R1_OK;
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return r1_set_error(R1_ERR_CUDA, "cannot load libnccl.so.2: %s", dlerror());
+#define R1_SYM(field, name) field = reinterpret_cast<decltype(field)>(dlsym(h, name)); if (!field) { dlclose(h); return r1_set_error(R1_ERR_CUDA, "libnccl.so.2 lacks %s", name); }
         R1_SYM(CommInitAll, "ncclCommInitAll") R1_SYM(CommDestroy, "ncclCommDestroy") R1_SYM(GroupStart, "ncclGroupStart")
         R1_SYM(GroupEnd, "ncclGroupEnd") R1_SYM(Send, "ncclSend") R1_SYM(Recv, "ncclRecv") R1_SYM(Reduce, "ncclReduce")
         R1_SYM(GetErrorString, "ncclGetErrorString")
 #undef R1_SYM
-        return true;
+        lib = h;   // published only once every symbol resolved
+        return R1_OK;
     }
 };
+
+#define R1H_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return r1_set_error(R1_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); } while (0)
+#define R1H_NCCL(expr) do { ncclResult_t r_ = (expr); if (r_ != ncclSuccess) return r1_set_error(R1_ERR_CUDA, "%s: %s", #expr, nccl.GetErrorString(r_)); } while (0)
+#define R1H_TRY(expr) do { int rc_ = (expr); if (rc_) return rc_; } while (0)
 
 struct MultiGpu {
     Nccl nccl;
@@ -251,56 +264,72 @@ struct MultiGpu {
     uint8_t *final_img = nullptr;        // device 0: full image
     size_t stride = 0, final_bytes = 0;
 
-    void check(cudaError_t e, const char *what)
+    void release()
     {
-        if (e != cudaSuccess) { fprintf(stderr, "rays1_b200: %s: %s\n", what, cudaGetErrorString(e)); exit(1); }
-    }
-    void check(ncclResult_t r, const char *what)
-    {
-        if (r != ncclSuccess) { fprintf(stderr, "rays1_b200: %s: %s\n", what, nccl.GetErrorString(r)); exit(1); }
-    }
-    void init(int n_gpus)
-    {
-        if (n == n_gpus) return;
-        if (n != 0) { fprintf(stderr, "rays1_b200: GPU count cannot change between renders (%d -> %d)\n", n, n_gpus); exit(1); }
-        if (!nccl.load()) { fprintf(stderr, "rays1_b200: cannot load libnccl.so.2: %s\n", dlerror()); exit(1); }
-        n = n_gpus;
-        std::vector<int> devs(n);
-        for (int i = 0; i < n; ++i) devs[i] = i;
-        comms.resize(n);
-        check(nccl.CommInitAll(comms.data(), n, devs.data()), "ncclCommInitAll");
-        streams.resize(n); rgb.assign(n, nullptr); rays.assign(n, nullptr); rays_sum.assign(n, nullptr);
         for (int i = 0; i < n; ++i) {
-            check(cudaSetDevice(i), "cudaSetDevice");
-            check(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking), "cudaStreamCreate");
-            check(cudaMalloc(&rays[i], 8), "cudaMalloc");
-            check(cudaMalloc(&rays_sum[i], 8), "cudaMalloc");
+            cudaSetDevice(i);
+            if (i < (int)streams.size() && streams[i]) cudaStreamDestroy(streams[i]);
+            if (i < (int)rgb.size() && rgb[i]) cudaFree(rgb[i]);
+            if (i < (int)rays.size() && rays[i]) cudaFree(rays[i]);
+            if (i < (int)rays_sum.size() && rays_sum[i]) cudaFree(rays_sum[i]);
+            if (i < (int)comms.size() && comms[i]) nccl.CommDestroy(comms[i]);
         }
+        if (n > 0) { cudaSetDevice(0); if (gathered) cudaFree(gathered); if (final_img) cudaFree(final_img); }
+        comms.clear(); streams.clear(); rgb.clear(); rays.clear(); rays_sum.clear();
+        gathered = final_img = nullptr; stride = final_bytes = 0; n = 0;
     }
-    void size_for(int width, int height, int row_tile)
+    // communicator, streams, counters for n_gpus devices; a different GPU count than last time re-initialises
+    int init(int n_gpus)
+    {
+        if (n == n_gpus) return R1_OK;
+        release();
+        R1H_TRY(nccl.load());
+        int visible = 0;
+        R1H_CUDA(cudaGetDeviceCount(&visible));
+        if (n_gpus > visible) return r1_set_error(R1_ERR_ARG, "%d GPUs requested, %d visible", n_gpus, visible);
+        std::vector<int> devs(n_gpus);
+        for (int i = 0; i < n_gpus; ++i) devs[i] = i;
+        comms.assign(n_gpus, nullptr);
+        R1H_NCCL(nccl.CommInitAll(comms.data(), n_gpus, devs.data()));
+        n = n_gpus;
+        streams.assign(n, nullptr); rgb.assign(n, nullptr); rays.assign(n, nullptr); rays_sum.assign(n, nullptr);
+        for (int i = 0; i < n; ++i) {
+            R1H_CUDA(cudaSetDevice(i));
+            R1H_CUDA(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
+            R1H_CUDA(cudaMalloc(&rays[i], 8));
+            R1H_CUDA(cudaMalloc(&rays_sum[i], 8));
+        }
+        return R1_OK;
+    }
+    int size_for(int width, int height, int row_tile)
     {
         size_t need = 0;
         for (int r = 0; r < n; ++r) need = std::max(need, (size_t)r1_local_pixels(width, height, row_tile, r, n) * 3);
         need = (need + 255) / 256 * 256;
         if (need > stride) {
             for (int i = 0; i < n; ++i) {
-                check(cudaSetDevice(i), "cudaSetDevice");
+                R1H_CUDA(cudaSetDevice(i));
                 if (rgb[i]) cudaFree(rgb[i]);
-                check(cudaMalloc(&rgb[i], need), "cudaMalloc");
+                rgb[i] = nullptr;
+                R1H_CUDA(cudaMalloc(&rgb[i], need));
             }
-            check(cudaSetDevice(0), "cudaSetDevice");
+            R1H_CUDA(cudaSetDevice(0));
             if (gathered) cudaFree(gathered);
-            check(cudaMalloc(&gathered, need * n), "cudaMalloc");
+            gathered = nullptr; stride = 0;
+            R1H_CUDA(cudaMalloc(&gathered, need * n));
             stride = need;
         }
         const size_t fb = (size_t)width * height * 3;
         if (fb > final_bytes) {
-            check(cudaSetDevice(0), "cudaSetDevice");
+            R1H_CUDA(cudaSetDevice(0));
             if (final_img) cudaFree(final_img);
-            check(cudaMalloc(&final_img, fb), "cudaMalloc");
+            final_img = nullptr; final_bytes = 0;
+            R1H_CUDA(cudaMalloc(&final_img, fb));
             final_bytes = fb;
         }
+        return R1_OK;
     }
+    int render(Scene *scene, Pix *pixels, uint64_t *num_rays, double *kernel_ms);
 };
 
 MultiGpu &multi_gpu()
@@ -309,78 +338,85 @@ MultiGpu &multi_gpu()
     return m;
 }
 
-RESULT render_multi(Scene *scene, Pix *pixels, int n_gpus, double *kernel_ms)
+// replaces TileRenderScheduler::run (rayweek1.cpp:788-842) for n > 1: trace on every device, gather, reduce, one D2H
+int MultiGpu::render(Scene *scene, Pix *pixels, uint64_t *num_rays, double *kernel_ms)
 {
     const HostConfig &cfg = host_config();
-    MultiGpu &m = multi_gpu();
-    m.init(n_gpus);
-    m.size_for(cfg.width, cfg.height, cfg.row_tile);
     r1_render_params p;
     memset(&p, 0, sizeof(p));
     p.width = cfg.width; p.height = cfg.height; p.spp = cfg.spp; p.max_bounces = cfg.max_bounces;
-    p.variant = cfg.variant; p.seed = cfg.seed; p.world = n_gpus; p.row_tile = cfg.row_tile;
+    p.variant = cfg.variant; p.seed = cfg.seed; p.world = n; p.row_tile = cfg.row_tile;
     // 1. every device traces its row tiles (asynchronous launches from this one host thread)
-    for (int r = 0; r < n_gpus; ++r) {
+    for (int r = 0; r < n; ++r) {
         p.rank = r; p.device = r;
-        if (r1_render_device(scene->handle, &p, m.rgb[r], m.rays[r], m.streams[r], nullptr)) die("r1_render_device");
+        R1H_TRY(r1_render_device(scene->handle, &p, rgb[r], rays[r], streams[r], nullptr));
     }
     // 2. framebuffer gather to rank 0 + ray-counter reduce: the path's only exchange step
-    m.check(m.nccl.GroupStart(), "ncclGroupStart");
-    for (int r = 0; r < n_gpus; ++r) {
-        const size_t bytes = (size_t)r1_local_pixels(cfg.width, cfg.height, cfg.row_tile, r, n_gpus) * 3;
-        m.check(m.nccl.Send(m.rgb[r], bytes, ncclUint8, 0, m.comms[r], m.streams[r]), "ncclSend");
-        m.check(m.nccl.Recv(m.gathered + (size_t)r * m.stride, bytes, ncclUint8, r, m.comms[0], m.streams[0]), "ncclRecv");
+    R1H_NCCL(nccl.GroupStart());
+    for (int r = 0; r < n; ++r) {
+        const size_t bytes = (size_t)r1_local_pixels(cfg.width, cfg.height, cfg.row_tile, r, n) * 3;
+        R1H_NCCL(nccl.Send(rgb[r], bytes, ncclUint8, 0, comms[r], streams[r]));
+        R1H_NCCL(nccl.Recv(gathered + (size_t)r * stride, bytes, ncclUint8, r, comms[0], streams[0]));
     }
-    m.check(m.nccl.GroupEnd(), "ncclGroupEnd");
-    m.check(m.nccl.GroupStart(), "ncclGroupStart");
-    for (int r = 0; r < n_gpus; ++r)
-        m.check(m.nccl.Reduce(m.rays[r], m.rays_sum[r], 1, ncclUint64, ncclSum, 0, m.comms[r], m.streams[r]), "ncclReduce");
-    m.check(m.nccl.GroupEnd(), "ncclGroupEnd");
+    R1H_NCCL(nccl.GroupEnd());
+    R1H_NCCL(nccl.GroupStart());
+    for (int r = 0; r < n; ++r) R1H_NCCL(nccl.Reduce(rays[r], rays_sum[r], 1, ncclUint64, ncclSum, 0, comms[r], streams[r]));
+    R1H_NCCL(nccl.GroupEnd());
     // 3. de-interleave on device 0, one D2H of the RGB8 image
-    m.check(cudaSetDevice(0), "cudaSetDevice");
-    if (r1_deinterleave_rows(0, m.gathered, m.stride, m.final_img, cfg.width, cfg.height, cfg.row_tile, n_gpus, m.streams[0])) die("r1_deinterleave_rows");
-    unsigned long long rays = 0;
-    m.check(cudaMemcpyAsync(pixels, m.final_img, (size_t)cfg.width * cfg.height * 3, cudaMemcpyDeviceToHost, m.streams[0]), "cudaMemcpyAsync");
-    m.check(cudaMemcpyAsync(&rays, m.rays_sum[0], 8, cudaMemcpyDeviceToHost, m.streams[0]), "cudaMemcpyAsync");
-    for (int r = n_gpus - 1; r >= 0; --r) {
-        m.check(cudaSetDevice(r), "cudaSetDevice");
-        m.check(cudaStreamSynchronize(m.streams[r]), "cudaStreamSynchronize");
+    R1H_CUDA(cudaSetDevice(0));
+    R1H_TRY(r1_deinterleave_rows(0, gathered, stride, final_img, cfg.width, cfg.height, cfg.row_tile, n, streams[0]));
+    unsigned long long total = 0;
+    R1H_CUDA(cudaMemcpyAsync(pixels, final_img, (size_t)cfg.width * cfg.height * 3, cudaMemcpyDeviceToHost, streams[0]));
+    R1H_CUDA(cudaMemcpyAsync(&total, rays_sum[0], 8, cudaMemcpyDeviceToHost, streams[0]));
+    for (int r = n - 1; r >= 0; --r) {
+        R1H_CUDA(cudaSetDevice(r));
+        R1H_CUDA(cudaStreamSynchronize(streams[r]));
     }
     double worst = 0;
-    for (int r = 0; r < n_gpus; ++r) {
+    for (int r = 0; r < n; ++r) {
         r1_result res;
-        if (r1_render_wait(scene->handle, r, &res)) die("r1_render_wait");
+        R1H_TRY(r1_render_wait(scene->handle, r, &res));
         worst = std::max(worst, res.kernel_ms);
     }
     *kernel_ms = worst;
-    RESULT out = { 0, rays, worst };
-    return out;
+    *num_rays = total;
+    return R1_OK;
 }
 
-}  // namespace
+double g_last_kernel_ms = 0;
 
-// rayweek1.cpp:845-927
-RESULT benchmark(Scene *scene, Pix *pixels, bool write_tga, const char *scene_name)
+// benchmark() with an error path.  Takes ownership of the scene in every case (rayweek1.cpp:905).
+int benchmark_impl(Scene *scene, Pix *pixels, size_t pixels_bytes, bool write_tga, const char *scene_name, RESULT *out)
 {
-    RESULT result = { 0, 0, 0 };
+    struct Owner { Scene *s; ~Owner() { delete s; } } owner{ scene };
     const HostConfig &cfg = host_config();
-    const auto t0 = std::chrono::steady_clock::now();  // Timer timer; (:848) -- scene construction is not timed
-
+    const size_t need = (size_t)cfg.width * (size_t)cfg.height * sizeof(Pix);
+    if (pixels_bytes < need)
+        return r1_set_error(R1_ERR_ARG, "pixels holds %zu bytes, the configured %dx%d image needs %zu", pixels_bytes, cfg.width, cfg.height, need);
     const int n_gpus = cfg.n_gpus > 0 ? cfg.n_gpus : 1;
+    // Set-up that the reference does not have (NCCL communicator, per-device staging) happens BEFORE the timer: the reference
+    // times worker spawn + render + join (rayweek1.cpp:848-891), never one-off initialisation.
+    if (n_gpus > 1) {
+        R1H_TRY(multi_gpu().init(n_gpus));
+        R1H_TRY(multi_gpu().size_for(cfg.width, cfg.height, cfg.row_tile));
+    }
+    RESULT result = { 0, 0 };
+    double kernel_ms = 0;
+    const auto t0 = std::chrono::steady_clock::now();  // Timer timer; (:848) -- scene construction is not timed
     if (n_gpus == 1) {
         r1_render_params p;
         memset(&p, 0, sizeof(p));
         p.width = cfg.width; p.height = cfg.height; p.spp = cfg.spp; p.max_bounces = cfg.max_bounces;
         p.variant = cfg.variant; p.seed = cfg.seed; p.rank = 0; p.world = 1; p.row_tile = cfg.row_tile; p.device = 0;
         r1_result res;
-        if (r1_render(scene->handle, &p, reinterpret_cast<uint8_t *>(pixels), &res)) die("r1_render");
+        R1H_TRY(r1_render(scene->handle, &p, reinterpret_cast<uint8_t *>(pixels), &res));
         result.num_rays = res.num_rays;
-        result.kernel_ms = res.kernel_ms;
+        kernel_ms = res.kernel_ms;
     } else {
-        double kms = 0;
-        result = render_multi(scene, pixels, n_gpus, &kms);
+        R1H_TRY(multi_gpu().render(scene, pixels, &result.num_rays, &kernel_ms));
     }
     result.elapsed_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();  // :891
+    g_last_kernel_ms = kernel_ms;
 
     const uint64_t total_samples = (uint64_t)cfg.width * (uint64_t)cfg.height * (uint64_t)cfg.spp;  // 64-bit, unlike :893
     if (!cfg.quiet) {
@@ -394,25 +430,37 @@ RESULT benchmark(Scene *scene, Pix *pixels, bool write_tga, const char *scene_na
         printf("threads:        %d/%u\n", n_gpus, (unsigned)(visible > 0 ? visible : 0));
         printf("tile size:      %dx%d\n", cfg.width, cfg.row_tile);
         // extra lines go AFTER the reference's lines
-        printf("gpu kernel ms:  %.3f\n", result.kernel_ms);
-        printf("kernel mrays/s: %0.2f\n", result.kernel_ms > 0 ? result.num_rays / (result.kernel_ms * 1e-3) / 1e6 : 0.0);
+        printf("gpu kernel ms:  %.3f\n", kernel_ms);
+        printf("kernel mrays/s: %0.2f\n", kernel_ms > 0 ? result.num_rays / (kernel_ms * 1e-3) / 1e6 : 0.0);
         printf("\n");
     }
-
-    delete scene;  // :905 -- benchmark() takes ownership
-
-    if (write_tga) {  // :907-912
+    if (write_tga) {  // :907-912 (the scene is deleted first there too, :905)
         char filename[128];
         snprintf(filename, sizeof(filename), "out_%s.tga", scene_name);
         tga_write_rgb24(filename, cfg.width, cfg.height, pixels);
     }
+    *out = result;
+    return R1_OK;
+}
+
+}  // namespace
+
+// rayweek1.cpp:845-927
+RESULT benchmark(Scene *scene, Pix *pixels, bool write_tga, const char *scene_name)
+{
+    RESULT result = { 0, 0 };
+    const HostConfig &cfg = host_config();
+    // the reference's caller owns SCREEN_W * SCREEN_H pixels (:960); there is no size to check on this surface
+    if (benchmark_impl(scene, pixels, (size_t)cfg.width * cfg.height * sizeof(Pix), write_tga, scene_name, &result)) die("benchmark");
     return result;
 }
+
+double benchmark_last_kernel_ms() { return g_last_kernel_ms; }
 
 // common.h:47-77
 void log_results(const char *version, const char *scene, const RESULT *results, int num_runs)
 {
-    RESULT result = { 0, 0, 0 };
+    RESULT result = { 0, 0 };
     for (int i = 0; i < num_runs; i++) {
         result.elapsed_seconds += results[i].elapsed_seconds;
         result.num_rays += results[i].num_rays;
@@ -497,30 +545,35 @@ void *r1_host_create_scene_from_file(const char *path, int commit)
 
 r1_scene *r1_host_scene_handle(void *scene) { return scene ? static_cast<Scene *>(scene)->handle : nullptr; }
 
-int r1_host_benchmark(void *scene, uint8_t *pixels, int write_tga, const char *scene_name, double *elapsed_seconds, uint64_t *num_rays,
-                      double *kernel_ms)
+int r1_host_benchmark(void *scene, uint8_t *pixels, uint64_t pixels_bytes, int write_tga, const char *scene_name, double *elapsed_seconds,
+                      uint64_t *num_rays, double *kernel_ms)
 {
-    if (!scene || !pixels || !scene_name) return R1_ERR_ARG;
-    const RESULT r = benchmark(static_cast<Scene *>(scene), reinterpret_cast<Pix *>(pixels), write_tga != 0, scene_name);
+    if (!scene) return r1_set_error(R1_ERR_ARG, "null scene");
+    if (!pixels || !scene_name) { delete static_cast<Scene *>(scene); return r1_set_error(R1_ERR_ARG, "null argument"); }
+    RESULT r = { 0, 0 };
+    const int rc = benchmark_impl(static_cast<Scene *>(scene), reinterpret_cast<Pix *>(pixels), (size_t)pixels_bytes, write_tga != 0, scene_name, &r);
+    if (rc) return rc;
     if (elapsed_seconds) *elapsed_seconds = r.elapsed_seconds;
     if (num_rays) *num_rays = r.num_rays;
-    if (kernel_ms) *kernel_ms = r.kernel_ms;
+    if (kernel_ms) *kernel_ms = g_last_kernel_ms;
     return R1_OK;
 }
 
 void r1_host_destroy_scene(void *scene) { delete static_cast<Scene *>(scene); }
 
-int r1_host_write_tga(const char *filename, int width, int height, uint8_t *pixels)
+int r1_host_write_tga(const char *filename, int width, int height, uint8_t *pixels, uint64_t pixels_bytes)
 {
-    if (!filename || !pixels || width <= 0 || height <= 0) return R1_ERR_ARG;
-    return tga_write_rgb24(filename, width, height, reinterpret_cast<Pix *>(pixels)) ? R1_OK : R1_ERR_ARG;
+    if (!filename || !pixels || width <= 0 || height <= 0 || width > 0xFFFF || height > 0xFFFF) return r1_set_error(R1_ERR_ARG, "bad argument");
+    if (pixels_bytes < (uint64_t)width * (uint64_t)height * 3) return r1_set_error(R1_ERR_ARG, "pixels holds %llu bytes, %dx%d needs %llu",
+                                                                                   (unsigned long long)pixels_bytes, width, height, (unsigned long long)width * height * 3);
+    return tga_write_rgb24(filename, width, height, reinterpret_cast<Pix *>(pixels)) ? R1_OK : r1_set_error(R1_ERR_ARG, "cannot write %s", filename);
 }
 
 int r1_host_log_results(const char *version, const char *scene, const double *elapsed_seconds, const uint64_t *num_rays, int num_runs)
 {
     if (!version || !scene || !elapsed_seconds || !num_rays || num_runs <= 0 || num_runs > 1024) return R1_ERR_ARG;
     std::vector<RESULT> r(num_runs);
-    for (int i = 0; i < num_runs; ++i) r[i] = RESULT{ elapsed_seconds[i], num_rays[i], 0 };
+    for (int i = 0; i < num_runs; ++i) r[i] = RESULT{ elapsed_seconds[i], num_rays[i] };
     log_results(version, scene, r.data(), num_runs);
     return R1_OK;
 }

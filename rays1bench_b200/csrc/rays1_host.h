@@ -22,11 +22,10 @@ struct HostConfig {
 };
 HostConfig &host_config();
 
-// common.h:36-45 (+ kernel_ms: CUDA-event time of the kernels, reported after the reference's lines)
+// common.h:36-45, field for field
 struct RESULT {
     double elapsed_seconds;
     uint64_t num_rays;
-    double kernel_ms;
 
     double get_mrays_per_sec() const { return elapsed_seconds ? (num_rays / elapsed_seconds / 1000000.0) : 0; }
 };
@@ -50,6 +49,22 @@ Scene *create_synth4096_scene();  // SURVEY.md 8d config 5; not in the reference
 Scene *create_scene_by_name(const char *name);
 Scene *create_scene_from_file(const char *path);  // text scene description (rays1_host.cpp); nullptr on error
 
+// rayweek1.cpp:845 -- `pixels` must hold host_config().width * height entries.  A CUDA / NCCL failure is fatal here (the
+// reference has no error path); the C-linkage form r1_host_benchmark (include/rays1_b200.h) returns an error code instead.
 RESULT benchmark(Scene *scene, Pix *pixels, bool write_tga, const char *scene_name);
+// CUDA-event time of the kernels of the last benchmark() call (what the reference's RESULT has no field for)
+double benchmark_last_kernel_ms();
 void log_results(const char *version, const char *scene, const RESULT *results, int num_runs);
 bool tga_write_rgb24(const char *filename, int width, int height, Pix *pixels);  // !!! swaps R and B in `pixels`
+
+// with RAYS1_REFERENCE_MAIN defined before this header, the reference's own main()
+// (src/latest/rayweek1.cpp:930-988) compiles UNCHANGED against it -- the two macros it reads from common.h:19-20 map to the
+// runtime configuration, and the libc headers rayweek1.cpp includes at its top are included here.
+// (The test suite builds and runs exactly that: INTEGRATION.md section 2.)
+#ifdef RAYS1_REFERENCE_MAIN
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#define SCREEN_W (host_config().width)
+#define SCREEN_H (host_config().height)
+#endif

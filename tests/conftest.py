@@ -31,6 +31,14 @@ def reflib():
 
 
 @pytest.fixture(scope="session")
+def reflib4096():
+    from cpu_checkers import RefLib
+    if not RefLib.available(4096):
+        pytest.skip("oracle/_ref/libref_rays1_4096.so not built (needs /root/reference)")
+    return RefLib(4096)
+
+
+@pytest.fixture(scope="session")
 def r1():
     import rays1bench_b200
     return rays1bench_b200
@@ -38,12 +46,12 @@ def r1():
 
 @pytest.fixture(scope="session")
 def golden_rays():
-    return {name: dict(np.load(os.path.join(GOLDEN, "rays_%s.npz" % name))) for name in SCENES}
+    return {name: dict(np.load(os.path.join(GOLDEN, "rays_%s.npz" % name))) for name in SCENES + ("synth4096",)}
 
 
 @pytest.fixture(scope="session")
 def golden_render():
-    return {name: dict(np.load(os.path.join(GOLDEN, "render_%s.npz" % name))) for name in SCENES}
+    return {name: dict(np.load(os.path.join(GOLDEN, "render_%s.npz" % name))) for name in SCENES + ("synth4096",)}
 
 
 @pytest.fixture(scope="session")

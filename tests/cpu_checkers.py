@@ -15,6 +15,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "librays1_oracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libref_rays1.so")
+REF4096_SO = os.path.join(ROOT, "oracle", "_ref", "libref_rays1_4096.so")  # MAX_SPHERES patched to 4096 (oracle/Makefile)
 REF_EXE = os.path.join(ROOT, "oracle", "_ref", "rays1_latest")
 
 _f = np.float32
@@ -141,8 +142,16 @@ class Oracle(_Checker):
         L.orc_scatter.argtypes = [C.c_void_p, C.c_int, _fp, _fp, _fp, _ip, _fp, _fp, _ip, _fp, _fp]
         L.orc_get_ray.argtypes = [C.c_void_p, C.c_int, _fp, _fp, _fp, _fp, _fp]
         L.orc_replay_pixels.argtypes = [C.c_void_p, C.c_int, _ip, C.c_int, C.c_int, C.c_int, C.c_int, _up, _up, _fp, _up]
+        L.orc_scene_set_camera.argtypes = [C.c_void_p, _fp]
+        L.orc_rsqrt12.restype = C.c_float
+        L.orc_rsqrt12.argtypes = [C.c_float]
+        L.orc_hw_rsqrtss.restype = C.c_float
+        L.orc_hw_rsqrtss.argtypes = [C.c_float]
         L.orc_render.restype = C.c_uint64
         L.orc_render.argtypes = [C.c_void_p, _bp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+
+    def scene_set_camera(self, s, cam22):
+        self.lib.orc_scene_set_camera(s, np.ascontiguousarray(cam22, _f))
 
     def scatter(self, s, dir_in, p, normal, index, rand_sphere, rand_u):
         n = len(index)
@@ -179,17 +188,22 @@ class Oracle(_Checker):
 
 
 class RefLib(_Checker):
-    @staticmethod
-    def available():
-        return os.path.exists(REF_SO)
+    """max_spheres=4096 selects the build whose Hitable::hit holds 4096 spheres (the one-line MAX_SPHERES patch of
+    rayweek1.cpp:174); it also knows the "synth4096" scene (BASELINE.json config 5)."""
 
-    def __init__(self):
-        super().__init__(REF_SO, "ref_", False)
+    @staticmethod
+    def available(max_spheres=1024):
+        return os.path.exists(REF4096_SO if max_spheres > 1024 else REF_SO)
+
+    def __init__(self, max_spheres=1024):
+        super().__init__(REF4096_SO if max_spheres > 1024 else REF_SO, "ref_", False)
         L = self.lib
+        assert L.ref_max_spheres() >= max_spheres
         L.ref_record_paths.restype = C.c_int
         L.ref_record_paths.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint32, _fp, _fp, _ip, _ip, _fp, _fp,
                                        _fp, _fp, _fp, _ip, _fp, _fp, _fp, _fp, _fp]
         L.ref_get_ray.argtypes = [C.c_void_p, C.c_int, _fp, _fp, C.c_uint32, _fp, _fp, _fp]
+        L.ref_hit_scatter.argtypes = [C.c_void_p, C.c_int, _fp, _fp, C.c_uint32, _ip, _fp, _fp, _fp, _fp, _fp, _ip, _fp, _fp]
         L.ref_render.restype = C.c_uint64
         L.ref_render.argtypes = [C.c_void_p, _bp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
         L.ref_hardware_concurrency.restype = C.c_int
@@ -205,6 +219,18 @@ class RefLib(_Checker):
                                         a["normal"], a["rand_sphere"], a["rand_u"], a["scat_ok"], a["atten"],
                                         a["scat_dir"], a["cam_su"], a["cam_tv"], a["cam_disk"])
         return {k: v[:got] for k, v in a.items()}
+
+    def hit_scatter(self, s, org, dir_, seed=9):
+        """Hitable::hit + Material::scatter for given rays; returns the record ref_record_paths writes per segment."""
+        org = np.ascontiguousarray(org, _f)
+        dir_ = np.ascontiguousarray(dir_, _f)
+        n = org.shape[0]
+        a = dict(org=org, dir=dir_, index=np.zeros(n, np.int32), t=np.zeros(n, _f), p=np.zeros((n, 3), _f), normal=np.zeros((n, 3), _f),
+                 rand_sphere=np.zeros((n, 3), _f), rand_u=np.zeros(n, _f), scat_ok=np.zeros(n, np.int32), atten=np.zeros((n, 3), _f),
+                 scat_dir=np.zeros((n, 3), _f))
+        self.lib.ref_hit_scatter(s, n, org, dir_, seed, a["index"], a["t"], a["p"], a["normal"], a["rand_sphere"], a["rand_u"],
+                                 a["scat_ok"], a["atten"], a["scat_dir"])
+        return a
 
     def get_ray(self, s, su, tv, seed=10001):
         n = len(su)

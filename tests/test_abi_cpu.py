@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(r1):
     exported = set(re.findall(r"\sT\s+(r1_\w+)", nm))
     assert declared <= exported, sorted(declared - exported)
     assert declared == set(r1.EXPORTED), sorted(declared ^ set(r1.EXPORTED))
-    assert r1.lib.r1_abi_version() == 1
+    assert r1.lib.r1_abi_version() == 2
 
 
 def test_library_is_built_for_sm100a_only(r1):
@@ -60,16 +60,19 @@ def test_scene_builders_match_oracle_bit_for_bit(r1, oracle, name):
     s.close()
 
 
-@pytest.mark.parametrize("name", SCENES)
+@pytest.mark.parametrize("name", SCENES + ("synth4096",))
 def test_scene_builders_match_reference_golden(r1, golden_rays, name):
+    """every SoA array -- centres, radius^2, 1/radius, albedo, fuzz / ior -- has the reference's exact bits (synth4096: the
+    MAX_SPHERES = 4096 build of the reference with the 4096-sphere builder on its own classes)"""
     s = r1.create_scene(name, commit=False)
     a, g = s.soa(), golden_rays[name]
-    for k in ("cx", "cy", "cz", "radius_sq", "inv_radius"):
+    for k in ("cx", "cy", "cz", "radius_sq", "inv_radius", "albedo", "param"):
         assert np.array_equal(bits(a[k]), bits(g["soa_" + k])), k
     assert np.array_equal(a["kind"], g["soa_kind"])
-    np.testing.assert_allclose(a["albedo"], g["soa_albedo"], rtol=2e-7, atol=1e-9)
-    np.testing.assert_allclose(a["param"], g["soa_param"], rtol=2e-7)
+    # the reference's camera constants are folded at compile time (gcc -ffast-math); the run-time evaluation is within 4 ulp
     np.testing.assert_allclose(s.camera(), g["camera"], rtol=1e-6, atol=4e-6)
+    s.set_camera_raw(g["camera"])
+    assert np.array_equal(bits(s.camera()), bits(g["camera"]))
     # placeholders: radius 0 at 999999999, no material (rayweek1.cpp:575-576); the hollow shell keeps inv_radius 0
     ph = a["kind"] == r1.MAT_NONE
     assert (a["cx"][ph] == np.float32(999999999)).all() and (a["inv_radius"][ph] == 0).all()
@@ -98,6 +101,40 @@ def test_scene_abi_argument_checking(r1):
     p.world = 0
     assert lib.r1_render(sc, C.byref(p), np.zeros(16 * 9 * 3, np.uint8), C.byref(res)) == -1
     lib.r1_scene_destroy(sc)
+
+
+def test_pixel_buffer_sizes_are_checked(r1, tmp_path):
+    """benchmark() / tga_write_rgb24() never write past a caller's buffer that is too small for the configured image"""
+    r1.configure(width=64, height=36, spp=1, quiet=True)
+    try:
+        s = r1.create_scene("small", commit=False)
+        with pytest.raises(ValueError, match="configured 64x36"):
+            r1.benchmark(s, np.zeros((10, 10, 3), np.uint8), False, "small")
+        assert s.count() == 8, "a rejected call does not consume the scene"
+        # the C entry point itself: too small -> R1_ERR_ARG, scene consumed, nothing written
+        import ctypes as C
+        ptr, s._ptr = s._ptr, None
+        small = np.full(300, 7, np.uint8)
+        rc = r1.lib.r1_host_benchmark(ptr, small, small.size, 0, b"small", None, None, None)
+        assert rc == -1 and b"needs 6912" in r1.lib.r1_last_error() and (small == 7).all()
+        with pytest.raises(ValueError):
+            r1.tga_write_rgb24(str(tmp_path / "x.tga"), 8, 8, np.zeros(100, np.uint8))
+        buf = np.zeros(100, np.uint8)
+        assert r1.lib.r1_host_write_tga(str(tmp_path / "x.tga").encode(), 8, 8, buf, buf.size) == -1
+        assert not (tmp_path / "x.tga").exists()
+    finally:
+        r1.configure(width=1280, height=720, spp=250, quiet=True)
+
+
+def test_header_declares_what_the_library_exports(r1):
+    """every function include/rays1_b200.h declares is exported by the library and bound by the Python module, and vice versa"""
+    hdr = open(os.path.join(ROOT, "include", "rays1_b200.h")).read()
+    declared = set(re.findall(r"\b(r1_[a-z0-9_]+)\s*\(", hdr)) - {"r1_scene", "r1_result", "r1_render_params"}
+    nm = subprocess.run(["nm", "-D", "--defined-only", r1.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (r1_[a-z0-9_]+)$", nm, re.M))
+    assert declared <= exported, declared - exported
+    assert declared == set(r1.EXPORTED), declared ^ set(r1.EXPORTED)
+    assert r1.lib.r1_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_a_gpu(r1):

@@ -14,6 +14,22 @@ from conftest import SCENES, rmse
 pytestmark = pytest.mark.gpu
 
 REL = 1e-5
+ALL = SCENES + ("synth4096",)   # synth4096 = BASELINE.json config 5; its fixtures come from the MAX_SPHERES = 4096 build of the reference
+
+
+def record(key, value):
+    """measured maxima, kept next to the run (gpurun_out/parity_errors.json) so that they can be quoted in profiles/"""
+    import json
+    from conftest import ROOT
+    path = os.path.join(ROOT, "gpurun_out", "parity_errors.json")
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        data = json.load(open(path)) if os.path.exists(path) else {}
+        data[key] = value
+        json.dump(data, open(path, "w"), indent=1, sort_keys=True)
+    except OSError:
+        pass
+    print("%s: %s" % (key, value))
 
 
 def bits(a):
@@ -32,7 +48,7 @@ def scenes(r1):
 # ---- hit() ----------------------------------------------------------------------------------------------------------
 
 @pytest.mark.parametrize("variant", ["mega", "coop", "scalar"])
-@pytest.mark.parametrize("name", SCENES)
+@pytest.mark.parametrize("name", ALL)
 def test_hit_matches_reference_golden(r1, scenes, golden_rays, name, variant):
     g = golden_rays[name]
     org = np.concatenate([g["seg_org"], g["edge_org"]])
@@ -115,20 +131,16 @@ def test_hit_empty_and_single(r1, scenes):
     assert idx[0] == 0 and t[0] == pytest.approx(5.5)
 
 
-def refraction_condition(soa, index, dir_in, normal):
-    """Error amplification of Dielectric::scatter when leaving a high-index sphere: refracted = k (d - n dt) - n sqrt(1 - k^2 (1 - dt^2))
-    with k = ior multiplies the float32 rounding of (1 - dt^2) by k^2.  The large scene has ior up to 24.2 (rayweek1.cpp:692) and the
-    reference's OWN result is 2.1e-5 away from the exactly-rounded answer there (measured on tests/golden), so the 1e-5 contract is
-    scaled by max(1, k^2 / 8) for those rays only; every other ray is held to 1e-5 flat."""
-    ior = soa["param"][index]
-    exiting = (soa["kind"][index] == 2) & ((dir_in * normal).sum(1) > 0)
-    k = np.where(exiting, ior, 1.0)
-    return np.maximum(1.0, k * k / 8.0)
-
-
 # ---- scatter() / camera -------------------------------------------------------------------------------------------------
+# Tolerance: 1e-5 FLAT for every material, every ior (north_star).  Stronger, and asserted: the device follows the association
+# of the reference's binary including its rsqrtss + Newton normalise (r1_device.cuh "scatter", "unit3"), so the scattered
+# direction, the attenuation and the flag are BIT-IDENTICAL to the reference's on every recorded ray.
 
-@pytest.mark.parametrize("name", SCENES)
+def per_material_max(err, kinds):
+    return {("lambert", "metal", "dielectric")[k]: float(err[kinds == k].max()) for k in (0, 1, 2) if (kinds == k).any()}
+
+
+@pytest.mark.parametrize("name", ALL)
 def test_scatter_matches_reference_golden(r1, scenes, golden_rays, name):
     g = golden_rays[name]
     m = (g["seg_index"] >= 0) & (g["seg_depth"] < 50)
@@ -137,22 +149,45 @@ def test_scatter_matches_reference_golden(r1, scenes, golden_rays, name):
     assert np.array_equal(ok, g["seg_scat_ok"][m])
     assert np.array_equal(bits(att), bits(g["seg_atten"][m])) or np.abs(att - g["seg_atten"][m]).max() < 1e-7
     err = np.abs(dout - g["seg_scat_dir"][m]).max(axis=1)
-    soa = scenes[name].soa()
-    kinds = soa["kind"][g["seg_index"][m]]
-    assert (err <= REL * refraction_condition(soa, g["seg_index"][m], g["seg_dir"][m], g["seg_normal"][m])).all(), \
-        "scatter direction off by %g" % err.max()
-    assert (err <= REL)[kinds != 2].all()
+    kinds = scenes[name].soa()["kind"][g["seg_index"][m]]
+    record("scatter_golden_max_abs_err/%s" % name, per_material_max(err, kinds))
+    assert (err <= REL).all(), "scatter direction off by %g" % err.max()
+    assert np.array_equal(bits(dout), bits(g["seg_scat_dir"][m])) and np.array_equal(bits(att), bits(g["seg_atten"][m]))
     for k in (0, 1, 2):
         assert (kinds == k).sum() > 20, "material %d under-sampled" % k
 
 
-@pytest.mark.parametrize("name", SCENES)
+@pytest.mark.parametrize("name", ("large", "synth4096"))
+def test_dielectric_exit_rays_match_reference_golden(r1, scenes, golden_rays, name):
+    """rays leaving the ior >= 5 dielectric spheres from inside (320 on the large scene, ior up to 24.2, rayweek1.cpp:692; 2704
+    on synth4096): hit() bit-identical, Dielectric::scatter within 1e-5 flat -- both the refracting rays, where
+    1 - k^2 (1 - dt^2) amplifies rounding by k^2 <= 585, and the totally reflected ones"""
+    g = golden_rays[name]
+    idx, t, p, n = scenes[name].trace_rays(g["diel_org"], g["diel_dir"])
+    assert np.array_equal(idx, g["diel_index"]) and len(idx) >= 200
+    assert np.array_equal(bits(t), bits(g["diel_t"])) and np.array_equal(bits(n), bits(g["diel_normal"])) and np.array_equal(bits(p), bits(g["diel_p"]))
+    soa = scenes[name].soa()
+    assert (soa["kind"][idx] == 2).all() and (soa["param"][idx] >= 5).all()
+    ok, att, dout = scenes[name].scatter(g["diel_dir"], p, n, idx, g["diel_rand_sphere"], g["diel_rand_u"])
+    assert ok.all() and (att == 1).all()
+    err = np.abs(dout - g["diel_scat_dir"]).max(axis=1)
+    refracted = (g["diel_scat_dir"] * g["diel_normal"]).sum(1) > 0
+    assert refracted.sum() >= 150 and (~refracted).sum() >= 100
+    record("scatter_dielectric_exit_max_abs_err/%s" % name, {"refracted": float(err[refracted].max()), "reflected": float(err[~refracted].max()),
+                                                              "max_ior": float(soa["param"][idx].max()), "rays": int(len(idx))})
+    assert (err <= REL).all(), err.max()
+    assert np.array_equal(bits(dout), bits(g["diel_scat_dir"]))
+
+
+@pytest.mark.parametrize("name", ALL)
 def test_scatter_matches_oracle_on_fresh_inputs(r1, scenes, oracle, name):
     rng = np.random.default_rng(99)
     n = 4000
     soa = scenes[name].soa()
     real = np.where(soa["inv_radius"] > 0)[0]
     idx = rng.choice(real, n).astype(np.int32)
+    diel = np.where((soa["kind"] == 2) & (soa["inv_radius"] > 0))[0]
+    idx[: n // 4] = rng.choice(diel, n // 4)                       # a quarter of the inputs on dielectrics of every ior, half of them exiting
     nrm = rng.normal(size=(n, 3)); nrm = (nrm / np.linalg.norm(nrm, axis=1, keepdims=True)).astype(np.float32)
     din = rng.normal(size=(n, 3)); din = (din / np.linalg.norm(din, axis=1, keepdims=True)).astype(np.float32)
     ctr = np.stack([soa["cx"][idx], soa["cy"][idx], soa["cz"][idx]], 1)
@@ -163,22 +198,26 @@ def test_scatter_matches_oracle_on_fresh_inputs(r1, scenes, oracle, name):
     want = oracle.scatter(so, din, p, nrm, idx, rs, ru)
     got = scenes[name].scatter(din, p, nrm, idx, rs, ru)
     oracle.scene_destroy(so)
-    # metal's return flag is dot(dir, n) > 0: ignore the sign within rounding of zero
-    dotn = (want[2] * nrm).sum(1)
-    firm = np.abs(dotn) > 1e-5
-    assert np.array_equal(got[0][firm], want[0][firm])
-    assert np.abs(got[1] - want[1]).max() < 1e-7
     err = np.abs(got[2] - want[2]).max(axis=1)
-    assert (err <= REL * refraction_condition(soa, idx, din, nrm)).all(), err.max()
+    record("scatter_fresh_vs_oracle_max_abs_err/%s" % name, per_material_max(err, soa["kind"][idx]))
+    assert (err <= REL).all(), err.max()
+    # the same arithmetic on both sides: the same bits, including Metal's dot(dir, n) > 0 decision
+    assert np.array_equal(got[0], want[0]) and np.array_equal(bits(got[1]), bits(want[1])) and np.array_equal(bits(got[2]), bits(want[2]))
 
 
-@pytest.mark.parametrize("name", SCENES)
+@pytest.mark.parametrize("name", ALL)
 def test_camera_rays_match_reference_golden(r1, scenes, golden_rays, name):
     g = golden_rays[name]
     m = g["seg_depth"] == 0
     org, d = scenes[name].get_ray(g["seg_cam_su"][m], g["seg_cam_tv"][m], g["seg_cam_disk"][m])
     assert np.abs(org - g["seg_org"][m]).max() <= REL * np.abs(g["seg_org"][m]).max()
     assert np.abs(d - g["seg_dir"][m]).max() <= REL
+    # with the reference's own camera constants (folded at compile time there, <= 4 ulp from ours) getRay is bit-identical
+    s = r1.create_scene(name)
+    s.set_camera_raw(g["camera"], device=0)
+    org, d = s.get_ray(g["seg_cam_su"][m], g["seg_cam_tv"][m], g["seg_cam_disk"][m])
+    s.close()
+    assert np.array_equal(bits(org), bits(g["seg_org"][m])) and np.array_equal(bits(d), bits(g["seg_dir"][m]))
 
 
 # ---- RNG ------------------------------------------------------------------------------------------------------------------------
@@ -203,35 +242,73 @@ def test_rng_is_counter_based_and_uniform(r1):
 
 # ---- the trace loop: statistics against the reference ------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("name", SCENES)
+@pytest.mark.parametrize("name", ALL)
 def test_image_rmse_and_rays_per_sample_vs_reference(r1, scenes, golden_render, ref_stats, name):
-    """matched high spp: reference 16384 spp (tests/golden) vs GPU 16384 spp at 320x180."""
+    """matched high spp: reference 16384 spp (tests/golden) vs GPU 16384 spp at 320x180.  synth4096 (config 5) is compared with
+    the reference built with MAX_SPHERES = 4096 (rayweek1.cpp:174), not with the oracle port."""
     g = golden_render[name]
     h, w = g["rgb"].shape[:2]
     spp = int(g["spp"])
     rgb, res = scenes[name].render(w, h, spp)
     e = rmse(rgb, g["rgb"])
-    assert e <= 1.0, "per-channel RMSE %.3f / 255 exceeds 1/255" % e
     rps = res.num_rays / (w * h * spp)
     ref = ref_stats["default_workload"][name]["rays_per_sample"]
+    ref_same = ref_stats["render"][name]["rays_per_sample"]        # the reference's own count for this very render
+    record("render_320x180x%d/%s" % (spp, name), {"rmse_per_channel_255": e, "rays_per_sample": rps, "reference_rays_per_sample": ref_same,
+                                                   "reference_rays_per_sample_1280x720": ref})
+    assert e <= 1.0, "per-channel RMSE %.3f / 255 exceeds 1/255" % e
     assert abs(rps / ref - 1) < 0.005, (rps, ref)
+    assert abs(rps / ref_same - 1) < 0.005, (rps, ref_same)
     assert res.num_samples == w * h * spp
     # no systematic bias per channel either
     bias = (rgb.astype(np.float64) - g["rgb"]).mean(axis=(0, 1))
     assert np.abs(bias).max() < 0.25, bias
 
 
-@pytest.mark.parametrize("name", SCENES)
+@pytest.mark.parametrize("name", ALL)
 def test_full_size_default_workload(r1, scenes, ref_stats, name):
-    """BASELINE.json configs 1-3 at full size: 1280x720x250, depth 50."""
+    """BASELINE.json configs 1-3 and 5 at full size: 1280x720x250, depth 50."""
     rgb, res = scenes[name].render(1280, 720, 250)
     ref = ref_stats["default_workload"][name]
-    assert abs(res.num_rays / np.mean(ref["num_rays"]) - 1) < 0.005
-    assert rgb.shape == (720, 1280, 3)
+    rps = res.num_rays / (1280 * 720 * 250)
+    record("rays_per_sample_1280x720x250/%s" % name, {"gpu": rps, "reference": ref["rays_per_sample"]})
+    assert abs(rps / ref["rays_per_sample"] - 1) < 0.005
+    assert rgb.shape == (720, 1280, 3) and res.num_samples == 1280 * 720 * 250
     # sky at the top of the picture (last rows: row 0 is the BOTTOM), gradient blue > red
     top = rgb[-20:].reshape(-1, 3).mean(0)
     assert top[2] > top[0] and top[2] > 200
     assert res.launches == 2 and res.kernel_ms > 0 and res.trace_ms <= res.kernel_ms
+
+
+def test_config4_4k_sample_counts_need_64_bits(r1, ref_stats, capfd):
+    """BASELINE.json config 4: large scene, 3840x2160, 1024 spp = 8 493 465 600 samples -- the count the reference itself
+    gets wrong (int arithmetic, rayweek1.cpp:893).  (a) rays per sample at 4K within 0.5 % of the reference's figure for this
+    scene (the camera keeps its 16:9 aspect, so the figure does not depend on the resolution); (b) one rank's share of the
+    8-GPU partition at the full 1024 spp; (c) the whole image through benchmark(): total samples and rays beyond 2^32."""
+    W, H, SPP = 3840, 2160, 1024
+    r1.configure(width=W, height=H, spp=SPP, max_bounces=50, variant=0, n_gpus=1, seed=0, quiet=False)
+    try:
+        scene = r1.create_large_scene()
+        ref = ref_stats["default_workload"]["large"]["rays_per_sample"]
+        rgb, res = scene.render(W, H, 16)
+        assert rgb.shape == (H, W, 3) and res.num_samples == W * H * 16
+        assert abs(res.num_rays / (W * H * 16) / ref - 1) < 0.005
+        part, rp = scene.render(W, H, SPP, rank=0, world=8)
+        assert part.shape == (270, W, 3) and rp.num_samples == W * 270 * SPP == 1061683200
+        assert abs(rp.num_rays / rp.num_samples / ref - 1) < 0.01          # an eighth of the rows (every 8th row)
+        capfd.readouterr()
+        pixels = np.zeros((H, W, 3), np.uint8)
+        out = r1.benchmark(scene, pixels, False, "large")                  # the reference-facing call; ~4 s of GPU time
+        lines = capfd.readouterr().out.splitlines()
+        assert "total samples:  %d" % (W * H * SPP) in lines and W * H * SPP == 8493465600 > 2 ** 32
+        assert "total rays:     %d" % out.num_rays in lines and out.num_rays > 2 ** 32
+        assert abs(out.num_rays / (W * H * SPP) / ref - 1) < 0.005
+        record("config4_3840x2160x1024", {"num_samples": W * H * SPP, "num_rays": int(out.num_rays), "rays_per_sample": out.num_rays / (W * H * SPP),
+                                          "kernel_ms": out.kernel_ms})
+        rows8 = [r1.global_row(lr, r1.DEFAULT_ROW_TILE, 0, 8) for lr in range(270)]
+        assert np.array_equal(pixels[rows8], part), "the 8-GPU share is a subset of the single-GPU picture, byte for byte"
+    finally:
+        r1.configure(width=1280, height=720, spp=250, quiet=True)
 
 
 @pytest.mark.parametrize("name", SCENES)
@@ -243,17 +320,6 @@ def test_wavefront_full_size_matches_megakernel(r1, scenes, name):
     part, rp = scenes[name].render(1280, 720, 32, variant=r1.VARIANT_WAVEFRONT, rank=1, world=4)
     rows = [r1.global_row(lr, r1.DEFAULT_ROW_TILE, 1, 4) for lr in range(part.shape[0])]
     assert np.array_equal(part, a[rows])
-
-
-def test_synth4096_against_oracle_render(r1, scenes, oracle):
-    """config 5: no reference image exists (MAX_SPHERES = 1024 in the reference, rayweek1.cpp:174) -> oracle render."""
-    w, h, spp = 96, 54, 64
-    so = oracle.scene_create("synth4096", w, h)
-    want, rays_o, _ = oracle.render(so, w, h, spp, threads=8)
-    oracle.scene_destroy(so)
-    rgb, res = scenes["synth4096"].render(w, h, spp * 8)
-    assert abs(res.num_rays / (w * h * spp * 8) / (rays_o / (w * h * spp)) - 1) < 0.02
-    assert rmse(rgb, want) < 9.0  # the oracle side has only 64 spp
 
 
 # ---- determinism / partition invariance --------------------------------------------------------------------------------
@@ -421,21 +487,29 @@ def test_scene_above_staging_limit(r1, tmp_path):
     s.close()
 
 
-@pytest.mark.parametrize("name", SCENES)
-def test_per_pixel_replay_matches_reference_color(r1, scenes, name):
-    """the GPU integrator (production scan / exact test / scatter / sky, reference generators replayed from
-    recorded states) against the colour the reference's own color() returned for the same 4096 samples.  Path-level parity:
-    RNG consumption order, depth logic, attenuation order, ray counting.  Fractions, not all(): one float-rounding flip of a
-    decision changes that sample (the oracle itself agrees with the reference on 98.9-100 % of these samples)."""
+@pytest.mark.parametrize("name", ALL)
+def test_per_pixel_replay_matches_reference_color(r1, scenes, golden_rays, name):
+    """the GPU integrator (production scan / exact test / scatter / sky, the reference's generators replayed
+    from recorded states) against the colour the reference's own color() returned for the same 4096 samples per scene.
+    Path-level parity: RNG consumption order, depth logic, attenuation order, ray counting.  With the reference's recorded
+    camera constants installed the result is BIT-IDENTICAL: every ray count and every float colour.  With the camera constants
+    evaluated at run time (<= 4 ulp away) primary rays differ in the last bit and a few percent of the samples take another
+    path (far hits are that sensitive), hence fractions for that case."""
     from conftest import GOLDEN
     g = dict(np.load(os.path.join(GOLDEN, "replay_%s.npz" % name)))
     col, rays = scenes[name].replay_pixels(g["xy"], 1280, 720, 1, g["state"], g["state4"])
     err = np.abs(col - g["color"]).max(axis=1)
     same_rays, close = float((rays == g["rays"]).mean()), float((err < 1e-3).mean())
-    assert same_rays >= 0.985 and close >= 0.992 and np.median(err) < 1e-6, (same_rays, close, float(np.median(err)))
-    assert abs(rays.mean() / g["rays"].mean() - 1) < 0.02   # 4096 samples, ~1 % of them flipped: the 0.5 % gate runs on 2e8 samples elsewhere
-    q = lambda c: (np.sqrt(np.maximum(c, 0)) * 255.99).astype(int)   # noqa: E731  -- the reference's quantisation of a 1-spp pixel
-    assert (q(col) == q(g["color"])).all(axis=1).mean() >= 0.98
+    assert same_rays >= 0.95 and close >= 0.95 and np.median(err) < 1e-6, (same_rays, close, float(np.median(err)))
+    s = r1.create_scene(name)
+    s.set_camera_raw(golden_rays[name]["camera"], device=0)
+    col, rays = s.replay_pixels(g["xy"], 1280, 720, 1, g["state"], g["state4"])
+    record("replay_4096_samples/%s" % name, {"same_ray_count": float((rays == g["rays"]).mean()),
+                                             "colour_bit_identical": float((bits(col) == bits(g["color"])).all(axis=1).mean()),
+                                             "with_runtime_camera_constants_same_ray_count": same_rays})
+    assert np.array_equal(rays, g["rays"])
+    assert np.array_equal(bits(col), bits(g["color"]))
     # depth cap honoured: with max_bounces = 3 no sample traces more than 4 rays
-    col3, rays3 = scenes[name].replay_pixels(g["xy"][:512], 1280, 720, 1, g["state"][:512], g["state4"][:512], max_bounces=3)
+    col3, rays3 = s.replay_pixels(g["xy"][:512], 1280, 720, 1, g["state"][:512], g["state4"][:512], max_bounces=3)
+    s.close()
     assert rays3.max() <= 4

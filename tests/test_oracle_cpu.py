@@ -8,6 +8,8 @@ import os
 
 from conftest import GOLDEN, SCENES, rmse
 
+ALL = SCENES + ("synth4096",)   # synth4096 = BASELINE.json config 5, recorded from the MAX_SPHERES = 4096 build of the reference
+
 
 def bits(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)
@@ -73,22 +75,22 @@ def test_pinhole_hits_known_answers(oracle):
 
 # ---- golden vectors recorded from the reference ------------------------------------------------------------------
 
-@pytest.mark.parametrize("name", SCENES)
+@pytest.mark.parametrize("name", ALL)
 def test_scene_soa_matches_reference(oracle, golden_rays, name):
     s = oracle.scene_create(name)
     soa, g = oracle.scene_soa(s), golden_rays[name]
-    assert oracle.scene_count(s) == len(g["soa_cx"]) == {"small": 8, "medium": 48, "large": 488}[name]
+    assert oracle.scene_count(s) == len(g["soa_cx"]) == {"small": 8, "medium": 48, "large": 488, "synth4096": 4096}[name]
     for k in ("cx", "cy", "cz", "radius_sq", "inv_radius"):
         assert np.array_equal(bits(soa[k]), bits(g["soa_" + k])), k
     assert np.array_equal(soa["kind"], g["soa_kind"])
-    # albedo / ior involve libc rand()/255.0f and 1.2f + i*0.05f: the fast-math reference rounds them differently by <= 1 ulp
-    np.testing.assert_allclose(soa["albedo"], g["soa_albedo"], rtol=2e-7, atol=1e-9)
-    np.testing.assert_allclose(soa["param"], g["soa_param"], rtol=2e-7)
+    # albedo / ior / fuzz: x / 255.0f, 1.2f + i * 0.05f, 0.01f + 0.5f * y / H evaluated the way the fast-math build does
+    assert np.array_equal(bits(soa["albedo"]), bits(g["soa_albedo"])) and np.array_equal(bits(soa["param"]), bits(g["soa_param"]))
+    # camera constants: gcc folds Camera::init at compile time; a run-time evaluation of rayweek1.cpp:366-379 is within 4 ulp
     np.testing.assert_allclose(oracle.scene_camera(s), g["camera"], rtol=1e-6, atol=4e-6)
     oracle.scene_destroy(s)
 
 
-@pytest.mark.parametrize("name", SCENES)
+@pytest.mark.parametrize("name", ALL)
 def test_hit_bit_exact_on_recorded_segments(oracle, golden_rays, name):
     g = golden_rays[name]
     s = oracle.scene_create(name)
@@ -102,7 +104,7 @@ def test_hit_bit_exact_on_recorded_segments(oracle, golden_rays, name):
     oracle.scene_destroy(s)
 
 
-@pytest.mark.parametrize("name", SCENES)
+@pytest.mark.parametrize("name", ALL)
 def test_hit_edge_rays(oracle, golden_rays, name):
     g = golden_rays[name]
     s = oracle.scene_create(name)
@@ -117,7 +119,7 @@ def test_hit_edge_rays(oracle, golden_rays, name):
     oracle.scene_destroy(s)
 
 
-@pytest.mark.parametrize("name", SCENES)
+@pytest.mark.parametrize("name", ALL)
 def test_scatter_matches_reference(oracle, golden_rays, name):
     g = golden_rays[name]
     s = oracle.scene_create(name)
@@ -126,14 +128,43 @@ def test_scatter_matches_reference(oracle, golden_rays, name):
                                    g["seg_rand_sphere"][m], g["seg_rand_u"][m])
     assert np.array_equal(ok, g["seg_scat_ok"][m])
     np.testing.assert_allclose(att, g["seg_atten"][m], rtol=2e-7, atol=1e-9)
-    # unit directions: 1e-5 (north_star); the reference normalises with rsqrt + one Newton step (-ffast-math)
-    assert np.abs(dout - g["seg_scat_dir"][m]).max() < 1e-5
+    np.testing.assert_array_equal(bits(att), bits(g["seg_atten"][m]))
+    # unit directions: the contract is 1e-5 (north_star).  The oracle follows the association of the reference's binary
+    # INCLUDING its normalise (rsqrtss table + one Newton step), so the directions are bit-identical for every material
+    np.testing.assert_array_equal(bits(dout), bits(g["seg_scat_dir"][m]))
     kinds = oracle.scene_soa(s)["kind"][g["seg_index"][m]]
     assert set(np.unique(kinds)) == {0, 1, 2}, "all three materials exercised"
     oracle.scene_destroy(s)
 
 
-@pytest.mark.parametrize("name", SCENES)
+@pytest.mark.parametrize("name", ("large", "synth4096"))
+def test_dielectric_exit_rays_match_reference(oracle, golden_rays, name):
+    """rays leaving the ior >= 5 spheres from inside (ior up to 24.2, rayweek1.cpp:692): hit() bit-exact, scatter() < 1e-6;
+    the source-order association (orc_set_as_built(0)) differs in the last bits and is shown to be the worse model"""
+    g = golden_rays[name]
+    s = oracle.scene_create(name)
+    idx, t, p, n = oracle.hit(s, g["diel_org"], g["diel_dir"])
+    assert np.array_equal(idx, g["diel_index"]) and (idx >= 0).all()
+    assert np.array_equal(bits(t), bits(g["diel_t"])) and np.array_equal(bits(n), bits(g["diel_normal"]))
+    soa = oracle.scene_soa(s)
+    assert (soa["kind"][idx] == 2).all() and (soa["param"][idx] >= 5).all() and len(idx) >= 200
+    assert ((g["diel_dir"] * g["diel_normal"]).sum(1) > 0).all(), "every ray leaves its sphere"
+    ok, att, dout = oracle.scatter(s, g["diel_dir"], g["diel_p"], g["diel_normal"], g["diel_index"], g["diel_rand_sphere"], g["diel_rand_u"])
+    assert ok.all() and np.array_equal(ok, g["diel_scat_ok"])
+    err = np.abs(dout - g["diel_scat_dir"]).max(axis=1)
+    np.testing.assert_array_equal(bits(dout), bits(g["diel_scat_dir"]))
+    refracted = (g["diel_scat_dir"] * g["diel_normal"]).sum(1) > 0
+    assert refracted.sum() >= 150 and (~refracted).sum() >= 100   # both branches of refract() are exercised
+    oracle.lib.orc_set_as_built(0)
+    try:
+        _, _, d0 = oracle.scatter(s, g["diel_dir"], g["diel_p"], g["diel_normal"], g["diel_index"], g["diel_rand_sphere"], g["diel_rand_u"])
+    finally:
+        oracle.lib.orc_set_as_built(1)
+    assert np.abs(d0 - g["diel_scat_dir"]).max() > err.max() == 0     # the source order is close (< 1e-5) but not the binary's arithmetic
+    oracle.scene_destroy(s)
+
+
+@pytest.mark.parametrize("name", ALL)
 def test_camera_rays_match_reference(oracle, golden_rays, name):
     g = golden_rays[name]
     s = oracle.scene_create(name)
@@ -141,22 +172,26 @@ def test_camera_rays_match_reference(oracle, golden_rays, name):
     org, d = oracle.get_ray(s, g["seg_cam_su"][m], g["seg_cam_tv"][m], g["seg_cam_disk"][m])
     assert np.abs(org - g["seg_org"][m]).max() < 2e-6
     assert np.abs(d - g["seg_dir"][m]).max() < 1e-6
+    # with the reference's own (compile-time folded) camera constants Camera::getRay is reproduced bit for bit
+    oracle.scene_set_camera(s, g["camera"])
+    org, d = oracle.get_ray(s, g["seg_cam_su"][m], g["seg_cam_tv"][m], g["seg_cam_disk"][m])
+    assert np.array_equal(bits(org), bits(g["seg_org"][m])) and np.array_equal(bits(d), bits(g["seg_dir"][m]))
     oracle.scene_destroy(s)
 
 
-@pytest.mark.parametrize("name", SCENES)
+@pytest.mark.parametrize("name", ALL)
 def test_render_statistics_match_reference(oracle, golden_render, ref_stats, name):
     """Oracle render (its own xorshift streams, 8 threads) vs the reference's 16384-spp render: noise-limited RMSE and the
     rays-per-sample figure within 0.5 % (north_star)."""
     g = golden_render[name]
     h, w = g["rgb"].shape[:2]
     s = oracle.scene_create(name, w, h)
-    spp = 48
+    spp = 48 if name != "synth4096" else 24   # 0.7 Mrays/s on 4096 spheres: keep the CPU suite short
     rgb, rays, _ = oracle.render(s, w, h, spp, threads=8)
     rps = rays / (w * h * spp)
     ref_rps = ref_stats["default_workload"][name]["rays_per_sample"]
     assert abs(rps / ref_rps - 1) < 0.005, (rps, ref_rps)
-    assert rmse(rgb, g["rgb"]) < 8.0
+    assert rmse(rgb, g["rgb"]) < (8.0 if name != "synth4096" else 11.0)
     oracle.scene_destroy(s)
 
 
@@ -209,16 +244,38 @@ def replay_agreement(col, rays, g):
     return float((rays == g["rays"]).mean()), float((err < 1e-3).mean()), float(np.median(err))
 
 
-@pytest.mark.parametrize("name", SCENES)
-def test_per_pixel_replay_matches_reference_color(oracle, name):
-    """the pixel loop driven by the reference's generators from recorded states reproduces the colour
-    the reference's own color() returned, sample by sample.  A float-rounding flip of one decision (grazing hit, Schlick
-    coin) changes that sample only; the large scene (ior up to 24) has ~1 % of those even between two builds of the
-    reference arithmetic, hence fractions instead of all()."""
+@pytest.mark.parametrize("name", ALL)
+def test_per_pixel_replay_matches_reference_color(oracle, golden_rays, name):
+    """the pixel loop driven by the reference's generators from recorded states reproduces the colour the
+    reference's own color() returned -- BIT FOR BIT, ray counts included, for all 4096 recorded samples per scene, once the
+    reference's compile-time folded camera constants are installed.  (With camera constants evaluated at run time, <= 4 ulp
+    away, primary rays differ in the last bit and 1-4 % of the samples take another path: far hits are that sensitive.)"""
     g = dict(np.load(os.path.join(GOLDEN, "replay_%s.npz" % name)))
     s = oracle.scene_create(name)
     col, rays = oracle.replay_pixels(s, g["xy"], 1280, 720, 1, g["state"], g["state4"])
     same_rays, close, med = replay_agreement(col, rays, g)
-    assert same_rays >= 0.985 and close >= 0.992 and med < 1e-6, (same_rays, close, med)
-    assert abs(rays.mean() / g["rays"].mean() - 1) < 0.02   # 4096 samples, ~1 % of them flipped: the 0.5 % gate runs on 2e8 samples elsewhere
+    assert same_rays >= 0.95 and close >= 0.95 and med < 1e-6, (same_rays, close, med)
+    oracle.scene_set_camera(s, golden_rays[name]["camera"])
+    col, rays = oracle.replay_pixels(s, g["xy"], 1280, 720, 1, g["state"], g["state4"])
+    assert np.array_equal(rays, g["rays"])
+    assert np.array_equal(bits(col), bits(g["color"]))
     oracle.scene_destroy(s)
+
+
+def test_rsqrt12_table_matches_this_cpu(oracle):
+    """the table behind the as-built normalise (rays1bench_b200/csrc/r1_rsqrt12_table.h) against the RSQRTSS instruction of the
+    CPU the tests run on.  Intel CPUs implement it as exactly this 2048-case table; other vendors differ within the
+    architectural 1.5 * 2^-12 bound, in which case the reference itself would behave differently there (skipped)."""
+    vendor = ""
+    try:
+        vendor = [l.split(":")[1].strip() for l in open("/proc/cpuinfo") if l.startswith("vendor_id")][0]
+    except (OSError, IndexError):
+        pass
+    rng = np.random.default_rng(5)
+    xs = np.concatenate([rng.uniform(1, 4, 20000), np.exp(rng.uniform(-60, 60, 20000)), [1.0, 2.0, 4.0, 0.25, 3.9999998, 1e-30, 1e30]]).astype(np.float32)
+    got = np.array([oracle.lib.orc_rsqrt12(float(x)) for x in xs], np.float32)
+    assert (np.abs(got * np.sqrt(xs.astype(np.float64)) - 1) <= 1.5 * 2.0 ** -12).all()
+    if vendor != "GenuineIntel":
+        pytest.skip("RSQRTSS table check needs an Intel CPU (this is %r)" % vendor)
+    hw = np.array([oracle.lib.orc_hw_rsqrtss(float(x)) for x in xs], np.float32)
+    assert np.array_equal(bits(got), bits(hw))

@@ -16,6 +16,11 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
+def fma32(a, b, c):
+    """float32 fma: the product of two float32 values is exact in float64, one rounding at the end"""
+    return np.float32(np.float64(np.float32(a)) * np.float64(np.float32(b)) + np.float64(np.float32(c)))
+
+
 def grid_scene(gw, gh, ior_mod, lookfrom, focus):
     """The reference's large-scene recipe; colours from glibc srand(111)/rand() like the C++ builders."""
     libc = ctypes.CDLL(None)
@@ -25,13 +30,14 @@ def grid_scene(gw, gh, ior_mod, lookfrom, focus):
     for y in range(gh):
         for x in range(gw):
             px, py, pz = f(x - gw // 2) * f(1.1), f(0), f(y - gh // 2) * f(1.1)
-            r, g, b = (f(libc.rand() & 0xff) / f(255.0) for _ in range(3))
+            # the constant expressions as the reference's fast-math build evaluates them (rays1_host.cpp:grid_scene)
+            r, g, b = (f(libc.rand() & 0xff) * (f(1.0) / f(255.0)) for _ in range(3))
             i = x + y * gw
             if i % 20 == 0:
                 k = i % ior_mod if ior_mod else i
-                spheres.append((px, py, pz, f(0.45), 2, 1, 1, 1, f(1.2) + f(k) * f(0.05)))
+                spheres.append((px, py, pz, f(0.45), 2, 1, 1, 1, fma32(k, 0.05, 1.2)))
             elif i % 10 == 0:
-                spheres.append((px, py + f(0.1), pz, f(0.45), 1, r, g, b, f(0.01) + f(0.5) * f(y) / f(gh)))
+                spheres.append((px, py + f(0.1), pz, f(0.45), 1, r, g, b, fma32(f(0.5) * f(y), f(1.0) / f(gh), 0.01)))
             else:
                 spheres.append((px, py, pz, f(0.45), 0, r, g, b, 0))
     spheres.append((0, f(-1000.5), 0, 1000, 0, 0.5, 0.5, 0.5, 0))

@@ -37,10 +37,17 @@ WORKLOADS = {
     "synth4096": ("synth4096", 1280, 720, 250, 50) # config 5
 }
 METRIC = "Mrays/s (large scene)"
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE megakernel launch, from the ncu --set full capture summarised in
-# profiles/r01_ncu_megakernel_large.md (capture E); null for workloads that were not captured
-NCU_TRAFFIC_BYTES = {("large", "mega"): 29593600 + 15104}  # capture E (final round-1 build): the 32-byte fixed-point pixel
-#                                                                accumulators read once after the L2 flush; they stay in L2 after
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the `ncu --set full` captures
+# summarised under profiles/; keyed "<workload>/<variant>" in profiles/ncu_traffic.json (null where nothing was captured)
+def ncu_traffic(workload, variant):
+    try:
+        table = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except (OSError, ValueError):
+        return None, None
+    e = table.get("%s/%s" % (workload, variant))
+    return (e["dram_bytes_per_launch"], e.get("source")) if e else (None, None)
+
+
 NOMINAL_SM_MHZ = 1965.0
 # the reference's own published figure for this metric and configuration (step13, large scene,
 # 1280x720, 250 spp) -- 59.362 Mrays/s on an i9-9900K 8c/16t, README.md:52 of the reference.  CPU hardware, quoted as published.
@@ -106,21 +113,100 @@ def reference_step(ref, scene, w, h, spp):
     return rays, el
 
 
+_NATIVE = None
+
+
+def native_build_usable():
+    global _NATIVE
+    if _NATIVE is None:
+        _NATIVE = _native_build_usable()
+    return _NATIVE
+
+
+def _native_build_usable():
+    """oracle/_ref/*_native* were built with the reference's exact line (bench.py:175: -flto -march=native) on the build
+    container's CPU; they may only run on a host that has every instruction-set flag that CPU had."""
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    try:
+        need = set(open(os.path.join(ref_dir, "native_cpu_flags.txt")).read().split())
+        have = set()
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("flags"):
+                have = set(line.split(":", 1)[1].split())
+                break
+        isa = {f for f in need if f.startswith(("avx", "sse", "ssse", "fma", "bmi", "adx", "aes", "pclmul", "sha", "vaes", "vpclmul", "gfni", "amx",
+                                                "movdir", "cldemote", "clwb", "clflushopt", "rdseed", "rdrand", "xsave", "fsgsbase", "f16c", "popcnt",
+                                                "lzcnt", "abm", "movbe", "serialize", "waitpkg", "pku", "rdpid", "enqcmd", "uintr", "ptwrite", "tsxldtrk"))}
+        march = open(os.path.join(ref_dir, "native_march.txt")).read().strip()
+        ok = isa <= have and os.path.exists(os.path.join(ref_dir, "libref_rays1_native.so"))
+        if ok:  # belt and braces: an illegal instruction must kill a throw-away process, not this one
+            probe = ("import sys; sys.path.insert(0, %r); from cpu_checkers import RefLib; r = RefLib(native=True); "
+                     "s = r.scene_create('small'); r.render(s, 64, 36, 1)" % os.path.join(ROOT, "tests"))
+            ok = subprocess.run([sys.executable, "-c", probe], capture_output=True, timeout=120).returncode == 0
+        return ok, march
+    except (OSError, subprocess.SubprocessError):
+        return False, None
+
+
+def reference_executable(budget_runs=3):
+    """the UNMODIFIED reference executable, `-n 3`, at its compiled-in workload (1280x720x250, small +
+    medium + large), threads = hardware_concurrency(); mean (what log_results writes, common.h:47-60) and best per scene."""
+    import re
+    import tempfile
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    usable, march = native_build_usable()
+    exe = os.path.join(ref_dir, "rays1_latest_native") if usable and os.path.exists(os.path.join(ref_dir, "rays1_latest_native")) else \
+        os.path.join(ref_dir, "rays1_latest")
+    if not os.path.exists(exe):
+        return None
+    with tempfile.TemporaryDirectory() as tmp:
+        t0 = time.time()
+        txt = subprocess.run([exe, "-n", str(budget_runs)], cwd=tmp, capture_output=True, text=True, timeout=900).stdout
+        wall = time.time() - t0
+    out, cur, threads = {}, None, None
+    for line in txt.splitlines():
+        if line.strip() in ("small", "medium", "large"):
+            cur = line.strip()
+        m = re.match(r"mrays/s:\s+([0-9.]+)", line)
+        if m and cur:
+            out.setdefault(cur, []).append(float(m.group(1)))
+        m = re.match(r"threads:\s+(\S+)", line)
+        if m:
+            threads = m.group(1)
+    return {"exe": os.path.basename(exe), "runs": budget_runs, "threads": threads, "wall_s": wall,
+            "build": "g++ 13.3 -pthread -ffast-math -O3 -g -fno-rtti -fno-exceptions -std=c++17 -flto -march=%s -m64 -DNDEBUG (bench.py:175 of the reference%s), "
+                     "built in the build container" % ((march, ", native = the container's CPU") if exe.endswith("_native") else ("x86-64-v3", "; no -flto")),
+            "mrays_per_s": {k: {"mean": sum(v) / len(v), "best": max(v)} for k, v in out.items()}}
+
+
 def cpu_reference(workload, budget_s, steps, warmup):
-    """Times the reference's CPU implementation (oracle/_ref = unmodified src/latest compiled in place; the oracle port
-    for the 4096-sphere scene the reference cannot hold) on a bounded sample of the workload.  Returns per-step results."""
+    """Times the reference's CPU implementation on a bounded sample of the workload: oracle/_ref = the unmodified src/latest
+    compiled in place (the MAX_SPHERES = 4096 build of the same sources for the 4096-sphere scene, which the reference cannot
+    hold otherwise), its own TileRenderScheduler on hardware_concurrency() threads.  The oracle port only where no reference
+    build is present.  Returns per-step results."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from cpu_checkers import Oracle, RefLib
     scene_name, w, h, spp, mb = WORKLOADS[workload]
     cores = os.cpu_count() or 1
-    if scene_name != "synth4096" and RefLib.available() and w * 9 == h * 16:
-        ref = RefLib()
+    build = None
+    if RefLib.available(4096 if scene_name == "synth4096" else 1024) and w * 9 == h * 16:
+        usable, march = native_build_usable()
+        if scene_name == "synth4096":
+            ref = RefLib(4096)
+            build = "-ffast-math -O3 -march=x86-64-v3, MAX_SPHERES = 4096 (rayweek1.cpp:174 patched in a temporary copy), built in the build container"
+        elif usable:
+            ref = RefLib(native=True)
+            build = "bench.py:175 of the reference verbatim: -ffast-math -O3 -flto -march=native (= %s, the build container's CPU)" % march
+        else:
+            ref = RefLib()
+            build = "-ffast-math -O3 -march=x86-64-v3 (this host lacks ISA flags of the native build), built in the build container"
         kind, scene = "reference", ref.scene_create(scene_name)
         cores = ref.hardware_concurrency()
         run = lambda s: reference_step(ref, scene, w, h, s)  # noqa: E731
     else:
         orc = Oracle()
         kind, scene = "port", orc.scene_create(scene_name, w, h)
+        build = "oracle/rays1_oracle.c (plain C restatement), -O2"
         def run(s):  # noqa: E306
             _, rays, el = orc.render(scene, w, h, s, mb, threads=cores)
             return rays, el
@@ -128,7 +214,8 @@ def cpu_reference(workload, budget_s, steps, warmup):
     sample_spp = int(max(1, min(spp, budget_s / max(el, 1e-3))))
     results = [run(sample_spp) for _ in range(warmup + steps)][warmup:]
     tot_rays, tot_s = sum(r for r, _ in results), sum(e for _, e in results)
-    return dict(kind=kind, cores=cores, sample="%s scene %dx%d at %d spp (%d of %d spp; Mrays/s does not depend on spp)" %
+    return dict(kind=kind, cores=cores, build=build, threads="%d/%d" % (cores, os.cpu_count() or cores),
+                sample="%s scene %dx%d at %d spp (%d of %d spp; Mrays/s does not depend on spp)" %
                 (scene_name, w, h, sample_spp, sample_spp, spp), value=tot_rays / tot_s / 1e6, ms_per_step=1e3 * tot_s / len(results),
                 rays_per_sample=tot_rays / (len(results) * w * h * sample_spp))
 
@@ -140,9 +227,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="large", choices=sorted(WORKLOADS))
-    ap.add_argument("--variant", default="mega", choices=["mega", "wavefront", "scalar", "coop"])
+    ap.add_argument("--variant", default="mega", choices=["mega", "wavefront", "scalar", "coop", "deferred"])
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work per reference step / baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-exe", action="store_true", help="skip the `rays1_latest -n 3` run of the unmodified reference executable")
     ap.add_argument("--threads", type=int, default=0, help="threads per persistent CTA (512/768/1024; 0 = library default)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -166,14 +254,22 @@ def main():
                 "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": r["value"] / PUBLISHED_MRAYS[args.workload] if args.workload in PUBLISHED_MRAYS else None,
                 "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": r["value"], "unit": "Mrays/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+                "cpu_baseline": {"value": r["value"], "unit": "Mrays/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                                 "build": r["build"], "threads": r["threads"]},
                 "e2e": {"value": r["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0, "rays_per_sample": r["rays_per_sample"]}
         print(json.dumps(line))
         return
 
     # -------------------------------------------------------------------------------------------- B200 arm
-    os.environ["NCCL_DEBUG"] = os.environ.get("R1_NCCL_DEBUG", "WARN")  # NCCL's version banner goes to stdout otherwise
+    # NCCL's INFO log (communicator ranks, transports, NVLS) stays ON: it is the evidence that N ranks really formed one
+    # communicator.  The image presets NCCL_DEBUG=VERSION (banner only), so anything quieter than INFO is raised to INFO; the log
+    # goes where NCCL sends it by default (stdout, like the version banner) -- the JSON line is still one line of its own,
+    # printed after every rank has gone quiet at a barrier.  R1_NCCL_DEBUG overrides.
+    if os.environ.get("R1_NCCL_DEBUG"):
+        os.environ["NCCL_DEBUG"] = os.environ["R1_NCCL_DEBUG"]
+    elif os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+        os.environ["NCCL_DEBUG"] = "INFO"
     import torch
     import torch.distributed as dist
 
@@ -184,8 +280,10 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- this path has no CPU implementation (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")  # host-side rendezvous for the in-process leg (no kernel spinning on the GPUs)
     variant = r1.VARIANTS[args.variant]
     row_tile = r1.DEFAULT_ROW_TILE
     r1.configure(width=W, height=H, spp=SPP, max_bounces=MB, variant=variant, n_gpus=1, seed=0, quiet=True)
@@ -259,7 +357,7 @@ def main():
     # ---- e2e: the reference-facing call with HOST buffers, every step = scene upload + render + download
     pixels_t = torch.zeros((H, W, 3), dtype=torch.uint8).pin_memory()
     pixels = pixels_t.numpy()
-    h2d = n_pad * (32 + 4 + 16 + 4)
+    h2d = n_pad * (32 + 32)   # scan + exact + 32-byte shading record per sphere
     d2h = W * H * 3 + 8
     e2e_s, e2e_rays = 0.0, 0
     for it in range(args.warmup + args.steps):
@@ -288,6 +386,35 @@ def main():
             e2e_s += dt
             e2e_rays += rays_step
 
+    # ---- e2e_inprocess (N > 1): the DROP-IN surface at N GPUs -- ONE process, configure(n_gpus=N) + create_<scene>_scene() +
+    # benchmark(scene, pixels, ...), i.e. rays1_host.cpp's MultiGpu path (ncclCommInitAll, grouped send/recv, ncclReduce) that
+    # replaces TileRenderScheduler::run.  Rank 0 drives all N devices while the other ranks wait on the HOST (gloo), their GPUs idle.
+    inproc = None
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)
+        if rank == 0:
+            torchrun_img = pixels.copy()
+            torchrun_rays = e2e_rays // max(args.steps, 1)
+            try:
+                r1.configure(width=W, height=H, spp=SPP, max_bounces=MB, variant=variant, n_gpus=world, seed=0, quiet=True)
+                ip_s, ip_rays, ip_kms = 0.0, 0, 0.0
+                for it in range(args.warmup + args.steps):
+                    t0 = time.perf_counter()
+                    sc = r1.create_scene(scene_name)                    # replicas on devices 0..N-1 (H2D)
+                    res = r1.benchmark(sc, pixels, False, scene_name)   # trace on N devices, gather, reduce, D2H
+                    dt = time.perf_counter() - t0
+                    if it >= args.warmup:
+                        ip_s += dt; ip_rays += res.num_rays; ip_kms += res.kernel_ms
+                inproc = {"value": ip_rays / ip_s / 1e6, "unit": "Mrays/s", "ms_per_step": 1e3 * ip_s / args.steps,
+                          "kernel_ms_per_step": ip_kms / args.steps, "api": "one process: configure(n_gpus=%d) + create_%s_scene() + benchmark()" % (world, scene_name),
+                          "image_equal_to_torchrun_path": bool(np.array_equal(pixels, torchrun_img)), "rays_equal": int(ip_rays // args.steps) == int(torchrun_rays)}
+            except r1.Rays1Error as e:
+                inproc = {"error": str(e)}
+            finally:
+                r1.configure(n_gpus=1)
+        dist.barrier(group=cpu_group)
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -309,9 +436,11 @@ def main():
                                (peak_scalar, peak_packed),
                 "peak_nominal": peak_nominal, "frac_nominal": achieved / peak_nominal,
                 "flops_per_ray": f_ray, "flops_model": "16 per ray-sphere test (FMA=2) x %d real spheres + 70 shading (SURVEY.md 8d)" % n_real,
-                "traffic": NCU_TRAFFIC_BYTES.get((args.workload, args.variant)) if world == 1 else None,
-                "traffic_note": "DRAM bytes per megakernel launch (ncu); algorithmic FLOPs are the REFERENCE's 16 per test, the filter "
-                                "executes 8 FMA-pipe instructions per test plus an exact re-test of the 0.4 % candidates",
+                "traffic": ncu_traffic(args.workload, args.variant)[0] if world == 1 else None,
+                "traffic_source": ncu_traffic(args.workload, args.variant)[1] if world == 1 else None,
+                "traffic_note": "DRAM bytes per launch of the dominant kernel (ncu --set full, profiles/ncu_traffic.json); algorithmic FLOPs are "
+                                "the REFERENCE's 16 per test, the filter executes 8 FMA-pipe instructions per test plus an exact re-test of "
+                                "the 0.4 % candidates",
                 "hbm": {"algorithmic_bytes_per_step": hbm_bytes, "achieved_gbs": hbm_bytes * args.steps / (ms_trace * 1e-3) / 1e9,
                         "note": "pixel accumulators (32 B, L2 atomics) + RGB8 out + sphere staging per CTA: HBM is idle on this path"}}
     try:
@@ -332,10 +461,20 @@ def main():
             "gpu_launches": launches, "roofline": roofline,
             "kernel_only": {"trace_ms_per_step": ms_trace / args.steps, "mrays_per_s": total_rays / (ms_trace * 1e-3) / 1e6},
             "rays_per_step": total_rays // args.steps, "rays_per_sample": total_rays / (args.steps * W * H * SPP)}
+    if inproc is not None:
+        line["e2e_inprocess"] = inproc
+    if world > 1:
+        line["nccl"] = {"nranks": world, "debug": os.environ.get("NCCL_DEBUG"), "debug_file": os.environ.get("NCCL_DEBUG_FILE")}
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference(args.workload, args.cpu_budget, 1, 0)
-        line["cpu_baseline"] = {"value": r["value"], "unit": "Mrays/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
-    print(json.dumps(line))
+        line["cpu_baseline"] = {"value": r["value"], "unit": "Mrays/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                                "build": r["build"], "threads": r["threads"]}
+        if scene_name in ("small", "medium", "large") and (W, H, SPP) == (1280, 720, 250) and not args.no_reference_exe:
+            exe = reference_executable(3)   # the unmodified executable, -n 3, mean and best
+            if exe:
+                line["cpu_baseline"]["executable_n3"] = exe
+    sys.stdout.flush()
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -39,8 +39,10 @@ enum {
     R1_VARIANT_MEGAKERNEL = 0, /* persistent threads, per-lane path state machine, per-lane packed f32x2 scan (fastest; default) */
     R1_VARIANT_WAVEFRONT = 1,  /* generate / intersect / shade kernels over compacted ray queues, CUDA-graph WHILE loop */
     R1_VARIANT_MEGAKERNEL_SCALAR = 2, /* A/B: megakernel with a per-lane scalar FFMA scan */
-    R1_VARIANT_MEGAKERNEL_COOP = 3    /* A/B: megakernel with the warp-cooperative scan (quads share sphere loads, candidates
+    R1_VARIANT_MEGAKERNEL_COOP = 3,   /* A/B: megakernel with the warp-cooperative scan (quads share sphere loads, candidates
                                          resolved through a per-warp shared-memory queue) */
+    R1_VARIANT_MEGAKERNEL_DEFERRED = 4 /* A/B: per-lane packed scan, candidates deferred to a per-warp queue and resolved once per
+                                         scan with every lane busy */
 };
 
 typedef struct r1_scene r1_scene; /* opaque: host SoA + per-device buffers */

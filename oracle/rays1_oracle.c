@@ -92,7 +92,7 @@ static inline float rsqrt12(float x)
     uint32_t xb, yb;
     memcpy(&xb, &x, 4);
     if (xb < 0x00800000u) return INFINITY;                                  /* zero / denormal (and negative: not used) */
-    yb = 0x3e800000u + ((uint32_t)k_rsqrt12[(xb >> 13) & 0x7ff] << 11) - ((((xb >> 23) - 127u) & ~1u) << 22);
+    yb = r1_rsqrt12_bits(xb, k_rsqrt12);   /* the one definition the CUDA kernels use too */
     float y;
     memcpy(&y, &yb, 4);
     return y;

@@ -162,12 +162,12 @@ Partition partition(int width, int height, int row_tile, int rank, int world)
 constexpr int kDefaultThreads = 1024;     // per-lane scans: 64 registers
 constexpr int kDefaultThreadsCoop = 512;  // cooperative scan: 4 rays per lane in flight, 127 registers
 
-template <int kScan, bool kStaged, int kThreads>
-int launch_megakernel_t(int sm_count, const r1::RenderArgs &args, const r1_render_params &prm, cudaStream_t stream)
+template <int kScan, bool kStaged, int kThreads, bool kRangeAcc>
+int launch_megakernel_tr(int sm_count, const r1::RenderArgs &args, const r1_render_params &prm, cudaStream_t stream)
 {
     constexpr int kBlocks = 1;
-    auto kern = r1::megakernel<kScan, kStaged, kThreads, kBlocks>;
-    const size_t smem = r1::kSmemSpheres + (kStaged ? (size_t)args.scene.n_pad * 32 : 0) + (kScan == r1::kScanCoop ? sizeof(r1::WarpScratch) * (kThreads / 32) : 0);
+    auto kern = r1::megakernel<kScan, kStaged, kThreads, kBlocks, kRangeAcc>;
+    const size_t smem = r1::kSmemSpheres + (kStaged ? (size_t)args.scene.n_pad * 32 : 0) + (kScan == r1::kScanCoop || kScan == r1::kScanLaneDeferred ? sizeof(r1::WarpScratch) * (kThreads / 32) : 0);
     R1_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = sm_count * kBlocks;
     if (prm.blocks_per_sm > 0) grid = sm_count * prm.blocks_per_sm;
@@ -177,6 +177,17 @@ int launch_megakernel_t(int sm_count, const r1::RenderArgs &args, const r1_rende
     kern<<<grid, kThreads, smem, stream>>>(args);
     R1_CUDA(cudaGetLastError());
     return R1_OK;
+}
+
+template <int kScan, bool kStaged, int kThreads>
+int launch_megakernel_t(int sm_count, const r1::RenderArgs &args, const r1_render_params &prm, cudaStream_t stream)
+{
+    // register-accumulated ranges only where lanes hold ranges (small scenes) and only for the default scan: the A/B variants
+    // keep the per-sample atomics, which also keeps "one atomic triple per sample" measurable (R1_RANGE_ACC=0 forces it)
+    static const bool allow = !(getenv("R1_RANGE_ACC") && atoi(getenv("R1_RANGE_ACC")) == 0);
+    if (kScan == r1::kScanLanePacked && kThreads == 1024 && args.sched_kmax > 1 && allow)
+        return launch_megakernel_tr<kScan == r1::kScanLanePacked ? kScan : r1::kScanLanePacked, kStaged, kThreads == 1024 ? kThreads : 1024, true>(sm_count, args, prm, stream);
+    return launch_megakernel_tr<kScan, kStaged, kThreads, false>(sm_count, args, prm, stream);
 }
 
 template <int kScan, bool kStaged>
@@ -198,7 +209,7 @@ int validate(const r1_render_params *p)
     // the pixel accumulators hold sums of radiance * 2^40 in 64 bits with samples clamped to 4.0 (r1_kernels.cuh): 2^22 samples
     // would wrap; 2^20 is the documented limit
     if (p->spp > (1 << 20)) return fail(R1_ERR_LIMIT, "spp %d exceeds the accumulator limit of 2^20 samples per pixel", p->spp);
-    if (p->variant < 0 || p->variant > 3) return fail(R1_ERR_ARG, "unknown variant %d", p->variant);
+    if (p->variant < 0 || p->variant > 4) return fail(R1_ERR_ARG, "unknown variant %d", p->variant);
     return R1_OK;
 }
 
@@ -346,14 +357,12 @@ int r1_scene_commit(r1_scene *scene, int device)
     const int n = (int)scene->cx.size();
     const int n_pad = (n + 15) / 16 * 16;  // one scan supergroup = 16 spheres (the reference pads to SIMD_WIDTH = 8, rayweek1.cpp:575)
     const float inf = std::numeric_limits<float>::infinity();
-    // host image of the device block: [scan n_pad f4 | exact n_pad f4 | mat n_pad f4 | inv_radius n_pad f | kind n_pad i32]
-    const size_t bytes = (size_t)n_pad * (16 + 16 + 16 + 4 + 4);
+    // host image of the device block: [scan n_pad f4 | exact n_pad f4 | shade n_pad x 2 f4]
+    const size_t bytes = (size_t)n_pad * (16 + 16 + 32);
     std::vector<unsigned char> host(bytes, 0);
     float *scan = reinterpret_cast<float *>(host.data());
     float4 *exact = reinterpret_cast<float4 *>(host.data()) + n_pad;
-    float4 *mat = exact + n_pad;
-    float *inv_r = reinterpret_cast<float *>(mat + n_pad);
-    int32_t *kind = reinterpret_cast<int32_t *>(inv_r + n_pad);
+    float4 *shade = exact + n_pad;
     for (int i = 0; i < n_pad; ++i) {
         const bool real = i < n && scene->inv_radius[i] != 0;  // rayweek1.cpp:288-292: inv_radius == 0 spheres never hit
         // supergroup layout (r1_device.cuh): group g = i / 4 at float4 index (g >> 2) * 16 + (g & 3); cy / cz / r2f at +4 / +8 / +12
@@ -371,13 +380,17 @@ int r1_scene_commit(r1_scene *scene, int device)
         } else {
             scan[4 * (f4 + 12) + k] = inf;
         }
-        kind[i] = R1_MAT_NONE;
+        int32_t kind = R1_MAT_NONE;
+        float inv_r = 0.0f;
         if (i < n) {
             exact[i] = make_float4(scene->cx[i], scene->cy[i], scene->cz[i], scene->radius_sq[i]);
-            mat[i] = make_float4(scene->albedo[3 * i], scene->albedo[3 * i + 1], scene->albedo[3 * i + 2], scene->param[i]);
-            inv_r[i] = scene->inv_radius[i];
-            kind[i] = scene->kind[i];
+            shade[2 * i] = make_float4(scene->albedo[3 * i], scene->albedo[3 * i + 1], scene->albedo[3 * i + 2], scene->param[i]);
+            inv_r = scene->inv_radius[i];
+            kind = scene->kind[i];
         }
+        float kind_bits;
+        memcpy(&kind_bits, &kind, 4);
+        shade[2 * i + 1] = make_float4(inv_r, kind_bits, 0.0f, 0.0f);
     }
     R1_CUDA(cudaMalloc(&c.block, bytes));
     {
@@ -387,9 +400,7 @@ int r1_scene_commit(r1_scene *scene, int device)
     float4 *d4 = reinterpret_cast<float4 *>(c.block);
     c.dev.scan = d4;
     c.dev.exact = d4 + n_pad;
-    c.dev.mat = d4 + 2 * (size_t)n_pad;
-    c.dev.inv_radius = reinterpret_cast<float *>(d4 + 3 * (size_t)n_pad);
-    c.dev.kind = reinterpret_cast<const int32_t *>(c.dev.inv_radius + n_pad);
+    c.dev.shade = d4 + 2 * (size_t)n_pad;
     c.dev.n_pad = n_pad;
     c.dev.n8 = (n + 7) / 8 * 8;
     c.dev.n_real = n;
@@ -507,6 +518,8 @@ int r1_render_device(r1_scene *scene, const r1_render_params *params, void *d_rg
                                                                   : launch_megakernel<r1::kScanLanePacked, false>(x.sm_count, a, prm, stream);
             else if (prm.variant == R1_VARIANT_MEGAKERNEL_COOP) rc = staged ? launch_megakernel<r1::kScanCoop, true>(x.sm_count, a, prm, stream)
                                                                             : launch_megakernel<r1::kScanCoop, false>(x.sm_count, a, prm, stream);
+            else if (prm.variant == R1_VARIANT_MEGAKERNEL_DEFERRED) rc = staged ? launch_megakernel<r1::kScanLaneDeferred, true>(x.sm_count, a, prm, stream)
+                                                                                : launch_megakernel<r1::kScanLaneDeferred, false>(x.sm_count, a, prm, stream);
             else rc = staged ? launch_megakernel<r1::kScanLaneScalar, true>(x.sm_count, a, prm, stream)
                              : launch_megakernel<r1::kScanLaneScalar, false>(x.sm_count, a, prm, stream);
             if (rc) return rc;
@@ -629,6 +642,7 @@ int r1_trace_rays(r1_scene *scene, int n, const float *org, const float *dir, fl
     };
     if (variant == R1_VARIANT_MEGAKERNEL_SCALAR) R1_TRY(launch(r1::trace_rays_kernel<r1::kScanLaneScalar>));
     else if (variant == R1_VARIANT_MEGAKERNEL_COOP) R1_TRY(launch(r1::trace_rays_kernel<r1::kScanCoop>));
+    else if (variant == R1_VARIANT_MEGAKERNEL_DEFERRED) R1_TRY(launch(r1::trace_rays_kernel<r1::kScanLaneDeferred>));
     else R1_TRY(launch(r1::trace_rays_kernel<r1::kScanLanePacked>));
     R1_CUDA(cudaGetLastError());
     R1_CUDA(cudaDeviceSynchronize());

@@ -11,14 +11,16 @@ constexpr unsigned kFull = 0xffffffffu;
 // Work decomposition: unit u = (local pixel lp, sample chunk c), u = lp * n_chunks + c: `samples_per_unit` consecutive
 // samples of one pixel (1 sample for spp <= 256).  Lanes take RANGES of consecutive units from one global counter --
 // 16 units at a time while there is plenty of work, down to 1 near the end, so the last lanes finish within one sample of
-// each other -- and add every finished sample to the pixel's accumulator in 64-bit FIXED POINT (2^-40) with a
+// each other -- and add every finished sample to the pixel's accumulator in 64-bit FIXED POINT (2^-24) with a
 // fire-and-forget atomic (RED.ADD.64).  Integer addition is associative: the sums, and therefore the RGB8 image, are
 // bit-identical for every GPU count, CTA shape, unit size and kernel variant, whatever order the samples arrive in.
-// (The reference sums floats sequentially per pixel, rayweek1.cpp:757-765; radiance per sample is in [0, 1], so 40
-// fractional bits lose < 1e-12 per sample and 2^20 samples fit.)
+// (The reference sums floats sequentially per pixel, rayweek1.cpp:757-765; radiance per sample is in [0, 1], so 24
+// fractional bits lose < 3e-8 per sample -- float32 itself resolves no better near 1 -- and 2^20 samples fit with room.)
+// Lanes that hold a RANGE of consecutive samples of one pixel (small scenes) first sum up to 32 quantised samples in three
+// 32-bit registers and flush once: integer sums, so the image bytes do not depend on who flushed what when.
 struct RenderArgs {
     DevScene scene;
-    unsigned long long *accum;       // npix_local x 4 (r, g, b, -): sum of per-sample radiance * 2^40
+    unsigned long long *accum;       // npix_local x 4 (r, g, b, -): sum of per-sample radiance * 2^24
     unsigned long long *num_rays;    // += one per traced ray (rayweek1.cpp:517)
     unsigned int *unit_counter;      // next unit to hand out
     uint8_t *rgb;                    // npix_local * 3, local rows packed, row 0 = bottom
@@ -33,8 +35,9 @@ struct RenderArgs {
 };
 
 constexpr int kSmemSpheres = 16 + R1_RSQRT12_ENTRIES * 2;   // megakernel: byte offset of the staged spheres (mbarrier, rsqrtss table first)
-constexpr float kFixedScale = 1099511627776.0f;            // 2^40
-constexpr float kFixedInvScale = 9.094947017729282e-13f;   // 2^-40
+constexpr float kFixedScale = 16777216.0f;                 // 2^24: one sample (clamped to 4.0) is < 2^26, so 32 samples sum in 32 bits
+constexpr float kFixedInvScale = 5.9604644775390625e-8f;   // 2^-24
+constexpr uint32_t kRangeFlush = 32;                       // register-accumulated samples per flush (range-scheduled scenes)
 
 // n / d for n, d < 2^32 with the precomputed magic (d == 1 -> magic 0)
 __device__ __forceinline__ uint32_t fast_div(uint32_t n, uint64_t magic) { return magic ? (uint32_t)__umul64hi((uint64_t)n, magic) : n; }
@@ -93,13 +96,21 @@ __device__ __forceinline__ void unit_begin(const RenderArgs &a, uint32_t unit, u
 }
 
 // one finished sample -> the pixel's fixed-point accumulator (order-free, see RenderArgs)
-__device__ __forceinline__ void accumulate_sample(const RenderArgs &a, uint32_t lp, f3 c)
+__device__ __forceinline__ uint32_t quantise_radiance(float c)
+{
+    // fmaxf(NaN, 0) = 0: a degenerate path (zero-length scatter direction) adds nothing instead of poisoning the sum
+    return __float2uint_rn(fminf(fmaxf(c, 0.0f), 4.0f) * kFixedScale);
+}
+__device__ __forceinline__ void accumulate_quantised(const RenderArgs &a, uint32_t lp, uint32_t r, uint32_t g, uint32_t b)
 {
     unsigned long long *dst = a.accum + (size_t)lp * 4;
-    // fmaxf(NaN, 0) = 0: a degenerate path (zero-length scatter direction) adds nothing instead of poisoning the sum
-    atomicAdd(dst + 0, __float2ull_rn(fminf(fmaxf(c.x, 0.0f), 4.0f) * kFixedScale));
-    atomicAdd(dst + 1, __float2ull_rn(fminf(fmaxf(c.y, 0.0f), 4.0f) * kFixedScale));
-    atomicAdd(dst + 2, __float2ull_rn(fminf(fmaxf(c.z, 0.0f), 4.0f) * kFixedScale));
+    atomicAdd(dst + 0, (unsigned long long)r);
+    atomicAdd(dst + 1, (unsigned long long)g);
+    atomicAdd(dst + 2, (unsigned long long)b);
+}
+__device__ __forceinline__ void accumulate_sample(const RenderArgs &a, uint32_t lp, f3 c)
+{
+    accumulate_quantised(a, lp, quantise_radiance(c.x), quantise_radiance(c.y), quantise_radiance(c.z));
 }
 
 // start sample s of a pixel: jitter (rayweek1.cpp:759), lens disk + camera ray (:760, :381-386)
@@ -127,9 +138,10 @@ __device__ __forceinline__ bool shade_step(const RenderArgs &a, int hit, float t
     if (depth >= a.max_bounces) return true;   // :523 -- no scatter (and no RNG draw) past the cap
     f3 p, n, atten, nd, rs = mk3(0, 0, 0);
     float ru = 0.0f;
-    hit_finalise(e, __ldg(a.scene.inv_radius + hit), o, d, t, p, n);
-    const int kind = __ldg(a.scene.kind + hit);
-    const float4 mat = __ldg(a.scene.mat + hit);
+    const ShadeRec sh = load_shade(a.scene, hit);
+    hit_finalise(e, sh.inv_radius, o, d, t, p, n);
+    const int kind = sh.kind;
+    const float4 mat = sh.mat;
     const uint32_t draw0 = kDrawsPrimary + kDrawsPerBounce * (uint32_t)depth;
     if (kind == 2) ru = rng.rand01(draw0);
     else rs = random_in_unit_sphere(rng, draw0);
@@ -144,9 +156,11 @@ __device__ __forceinline__ bool shade_step(const RenderArgs &a, int hit, float t
 // every scan with a live ray and divergence is confined to the short fetch / generate / shade steps.
 // Replaces render_tile + color + TileRenderScheduler (rayweek1.cpp:722-842, 515-536).
 // kScan: which Hitable::hit implementation the lanes run
-enum ScanKind { kScanCoop = 0, kScanLanePacked = 1, kScanLaneScalar = 2 };
+enum ScanKind { kScanCoop = 0, kScanLanePacked = 1, kScanLaneScalar = 2, kScanLaneDeferred = 3 };
 
-template <int kScan, bool kStaged, int kThreads, int kBlocksPerSM>
+// kRangeAcc: lanes sum the samples of their unit range in registers and flush per pixel / per 32 samples (scenes scheduled
+// with ranges, i.e. sched_kmax > 1); false = one atomic triple per sample (scan-heavy scenes, one unit per fetch)
+template <int kScan, bool kStaged, int kThreads, int kBlocksPerSM, bool kRangeAcc = false>
 __global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel(const __grid_constant__ RenderArgs a)
 {
     // shared memory: [mbarrier 16 B | rsqrtss table 4 KB | staged spheres n_pad * 32 B | per-warp scratch (cooperative scan)]
@@ -179,6 +193,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel(const __gri
     f3 o = mk3(0.0f, 1.0e18f, 0.0f), d = mk3(0.0f, 0.0f, 0.0f);  // idle lanes scan a ray that passes no filter
     Rng rng;
     rng.k0 = 0; rng.k1 = 0;
+    uint32_t acc_r = 0, acc_g = 0, acc_b = 0, acc_n = 0;       // kRangeAcc: quantised radiance of up to kRangeFlush samples of pixel lp
     const uint32_t lanes_x4 = gridDim.x * blockDim.x * a.sched_div;
 
     for (;;) {
@@ -223,6 +238,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel(const __gri
         float t = kTMax;
         int hit = -1;
         if (kScan == kScanCoop) scan_coop<(kThreads <= 512 ? 2 : 1)>(*ws, s_scan, s_exact, n_pad, o, d, kTMin, kTMax, t, hit);
+        else if (kScan == kScanLaneDeferred) scan_deferred(*reinterpret_cast<DeferScratch *>(ws), s_scan, s_exact, a.scene.n8, o, d, kTMin, kTMax, t, hit);
         else scan<kScan == kScanLanePacked>(s_scan, s_exact, a.scene.n8, o, d, kTMin, t, hit);
 
         // -- color() body (rayweek1.cpp:515-536)
@@ -231,17 +247,30 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel(const __gri
             f3 contrib;
             const float4 e = hit >= 0 ? s_exact[hit] : make_float4(0, 0, 0, 0);
             if (shade_step(a, hit, t, e, tab, o, d, thr, depth, rng, contrib)) {
-                accumulate_sample(a, lp, contrib);
+                const uint32_t lp_done = lp;
+                bool flush = false;
+                if (kRangeAcc) {
+                    acc_r += quantise_radiance(contrib.x); acc_g += quantise_radiance(contrib.y); acc_b += quantise_radiance(contrib.z);
+                    flush = ++acc_n == kRangeFlush;
+                } else {
+                    accumulate_sample(a, lp, contrib);
+                }
                 need_primary = true;
                 if (++s == s_end) {                          // unit done: the next one of my range, or a new range
                     if (++unit == unit_end) {
                         active = false;
+                        flush = true;
                         o = mk3(0.0f, 1.0e18f, 0.0f); d = mk3(0.0f, 0.0f, 0.0f);
                     } else if (s == a.spp) {
+                        flush = true;
                         unit_begin(a, unit, lp, pixel, fx, fy, s, s_end);   // first chunk of the next pixel
                     } else {
                         s_end = min(s + a.samples_per_unit, a.spp);        // next chunk of the same pixel
                     }
+                }
+                if (kRangeAcc && flush) {
+                    accumulate_quantised(a, lp_done, acc_r, acc_g, acc_b);
+                    acc_r = acc_g = acc_b = acc_n = 0;
                 }
             }
         }
@@ -300,10 +329,11 @@ __global__ void __launch_bounds__(128) trace_rays_kernel(const __grid_constant__
     float t = t_max;
     int hit = -1;
     if (kScan == kScanCoop) scan_coop<2>(*ws, s_spheres, s_spheres + sc.n_pad, sc.n_pad, o, d, t_min, t_max, t, hit);
+    else if (kScan == kScanLaneDeferred) scan_deferred(*reinterpret_cast<DeferScratch *>(ws), s_spheres, s_spheres + sc.n_pad, sc.n8, o, d, t_min, t_max, t, hit);
     else scan<kScan == kScanLanePacked>(s_spheres, s_spheres + sc.n_pad, sc.n8, o, d, t_min, t, hit);
     if (!live) return;
     f3 p = mk3(0, 0, 0), nrm = mk3(0, 0, 0);
-    if (hit >= 0) hit_finalise(s_spheres[sc.n_pad + hit], sc.inv_radius[hit], o, d, t, p, nrm);
+    if (hit >= 0) hit_finalise(s_spheres[sc.n_pad + hit], load_shade(sc, hit).inv_radius, o, d, t, p, nrm);
     index[k] = hit;
     t_out[k] = hit >= 0 ? t : 0.0f;
     p_out[3 * k] = p.x; p_out[3 * k + 1] = p.y; p_out[3 * k + 2] = p.z;
@@ -318,8 +348,9 @@ __global__ void scatter_kernel(const __grid_constant__ DevScene sc, int n, const
     const int i = index[k];
     f3 a = mk3(0, 0, 0), dd = mk3(0, 0, 0);
     bool r = false;
-    if (i >= 0 && i < sc.n_pad && sc.kind[i] >= 0)
-        r = scatter(sc.kind[i], sc.mat[i], mk3(dir_in[3 * k], dir_in[3 * k + 1], dir_in[3 * k + 2]), mk3(p[3 * k], p[3 * k + 1], p[3 * k + 2]),
+    const ShadeRec sh = load_shade(sc, i >= 0 && i < sc.n_pad ? i : 0);
+    if (i >= 0 && i < sc.n_pad && sh.kind >= 0)
+        r = scatter(sh.kind, sh.mat, mk3(dir_in[3 * k], dir_in[3 * k + 1], dir_in[3 * k + 2]), mk3(p[3 * k], p[3 * k + 1], p[3 * k + 2]),
                     mk3(nrm[3 * k], nrm[3 * k + 1], nrm[3 * k + 2]), mk3(rs[3 * k], rs[3 * k + 1], rs[3 * k + 2]), ru[k], g_rsqrt12, a, dd);
     ok[k] = r ? 1 : 0;
     atten[3 * k] = a.x; atten[3 * k + 1] = a.y; atten[3 * k + 2] = a.z;
@@ -405,8 +436,9 @@ __global__ void __launch_bounds__(128) replay_pixels_kernel(const __grid_constan
             if (depth >= max_bounces) break;
             f3 p, nrm, atten, nd, rs = mk3(0, 0, 0);
             float ru = 0.0f;
-            hit_finalise(s_exact[hit], sc.inv_radius[hit], o, d, t, p, nrm);
-            const int kind = sc.kind[hit];
+            const ShadeRec sh = load_shade(sc, hit);
+            hit_finalise(s_exact[hit], sh.inv_radius, o, d, t, p, nrm);
+            const int kind = sh.kind;
             if (kind == 2) {
                 ru = rng.rand01();                                                     // Dielectric: one scalar draw (:503)
             } else {
@@ -416,7 +448,7 @@ __global__ void __launch_bounds__(128) replay_pixels_kernel(const __grid_constan
                     rs = mk3(fsub(r4[0], 1.0f), fsub(r4[1], 1.0f), fsub(r4[2], 1.0f));
                 } while (fadd(fadd(fmul(rs.x, rs.x), fmul(rs.y, rs.y)), fmul(rs.z, rs.z)) >= 1.0f);
             }
-            if (!scatter(kind, sc.mat[hit], d, p, nrm, rs, ru, g_rsqrt12, atten, nd)) break;
+            if (!scatter(kind, sh.mat, d, p, nrm, rs, ru, g_rsqrt12, atten, nd)) break;
             stack[depth++] = atten;
             o = p; d = nd;
         }

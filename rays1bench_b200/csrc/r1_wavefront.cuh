@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kThreads, 1) wf_intersect(const __grid_constan
                 ++nrays;
                 w.slots[(size_t)slot * 4].w = t[r];                       // same 32-byte sector as the ray
                 w.slots[(size_t)slot * 4 + 1].w = __int_as_float(hit[r]);
-                cls = hit[r] < 0 ? 0 : 1 + __ldg(a.scene.kind + hit[r]);
+                cls = hit[r] < 0 ? 0 : 1 + __float_as_int(__ldg(a.scene.shade + 2 * hit[r] + 1).y);
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {          // ballot + popc compaction: one atomic per warp per class

@@ -16,6 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "librays1_oracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libref_rays1.so")
 REF4096_SO = os.path.join(ROOT, "oracle", "_ref", "libref_rays1_4096.so")  # MAX_SPHERES patched to 4096 (oracle/Makefile)
+REF_NATIVE_SO = os.path.join(ROOT, "oracle", "_ref", "libref_rays1_native.so")  # timing build: the reference's exact flags (-flto -march=native)
 REF_EXE = os.path.join(ROOT, "oracle", "_ref", "rays1_latest")
 
 _f = np.float32
@@ -195,8 +196,8 @@ class RefLib(_Checker):
     def available(max_spheres=1024):
         return os.path.exists(REF4096_SO if max_spheres > 1024 else REF_SO)
 
-    def __init__(self, max_spheres=1024):
-        super().__init__(REF4096_SO if max_spheres > 1024 else REF_SO, "ref_", False)
+    def __init__(self, max_spheres=1024, native=False):
+        super().__init__(REF4096_SO if max_spheres > 1024 else (REF_NATIVE_SO if native else REF_SO), "ref_", False)
         L = self.lib
         assert L.ref_max_spheres() >= max_spheres
         L.ref_record_paths.restype = C.c_int

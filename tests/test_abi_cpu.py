@@ -310,3 +310,29 @@ def test_bench_reference_arm_json_contract():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == d["value"] and "spp" in cb["sample"]
     assert d["gpu_launches"] == 0 and 1.7 < d["rays_per_sample"] < 1.9   # small scene: 1.798 rays per sample (ref_stats.json)
+
+
+def test_reference_main_compiles_unchanged_against_the_host_header(r1):
+    """the reference's own main() (rayweek1.cpp:930-988), not a line changed, compiles against
+    csrc/rays1_host.h (with RAYS1_REFERENCE_MAIN: SCREEN_W / SCREEN_H map to the run-time configuration) and links with the
+    product library.  Built by oracle/Makefile from the reference where it lies; without a GPU the result refuses to render."""
+    ref_main = os.path.join(ROOT, "oracle", "_ref", "rays1_refmain_b200")
+    if os.path.exists("/root/reference/src/latest/rayweek1.cpp"):
+        if os.path.exists(ref_main):
+            os.remove(ref_main)
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "refmain"], check=True, capture_output=True)
+    if not os.path.exists(ref_main):
+        pytest.skip("oracle/_ref/rays1_refmain_b200 not built (needs /root/reference)")
+    ldd = subprocess.run(["ldd", ref_main], capture_output=True, text=True).stdout
+    assert "librays1_b200.so" in ldd and "not found" not in ldd
+    nm = subprocess.run(["nm", "-D", "-C", ref_main], capture_output=True, text=True).stdout
+    for sym in ("create_small_scene()", "create_medium_scene()", "create_large_scene()", "benchmark(Scene*, Pix*, bool, char const*)",
+                "log_results(char const*, char const*, RESULT const*, int)"):
+        assert re.search(r"\bU %s" % re.escape(sym), nm), sym   # resolved from the product library, same C++ signatures
+    try:
+        n = r1.device_count()
+    except r1.Rays1Error:
+        n = 0
+    if n == 0:
+        out = subprocess.run([ref_main, "-n", "1"], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 1 and "rays1_b200: create_small_scene" in out.stderr, "no device -> fatal, never a CPU render"

@@ -47,7 +47,7 @@ def scenes(r1):
 
 # ---- hit() ----------------------------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("variant", ["mega", "coop", "scalar"])
+@pytest.mark.parametrize("variant", ["mega", "coop", "scalar", "deferred"])
 @pytest.mark.parametrize("name", ALL)
 def test_hit_matches_reference_golden(r1, scenes, golden_rays, name, variant):
     g = golden_rays[name]
@@ -93,7 +93,7 @@ def test_hit_matches_oracle_on_fresh_rays(r1, scenes, oracle, name):
     oracle.scene_destroy(so)
 
 
-@pytest.mark.parametrize("variant", ["mega", "coop", "scalar"])
+@pytest.mark.parametrize("variant", ["mega", "coop", "scalar", "deferred"])
 @pytest.mark.parametrize("name", ("large", "synth4096"))
 def test_filter_is_conservative_for_far_and_grazing_rays(r1, scenes, oracle, name, variant):
     """The 8-instruction filter works in the expanded form (cancellation at |o|^2 + |c|^2): rays from far away that graze
@@ -331,7 +331,7 @@ def test_bitwise_invariance(r1, scenes):
     base, r0 = s.render(w, h, spp)
     again, r1_ = s.render(w, h, spp)
     assert np.array_equal(base, again) and r0.num_rays == r1_.num_rays
-    for v in (r1.VARIANT_MEGAKERNEL_SCALAR, r1.VARIANT_MEGAKERNEL_COOP):
+    for v in (r1.VARIANT_MEGAKERNEL_SCALAR, r1.VARIANT_MEGAKERNEL_COOP, r1.VARIANT_MEGAKERNEL_DEFERRED):
         alt, ra = s.render(w, h, spp, variant=v)
         assert np.array_equal(base, alt) and ra.num_rays == r0.num_rays, v
     more, rm = s.render(w, h, spp, blocks_per_sm=2)
@@ -417,6 +417,28 @@ def test_drop_in_executable(r1, tmp_path):
         assert os.path.getsize(tmp_path / ("out_%s.tga" % name)) == 18 + 1280 * 720 * 3
 
 
+def test_reference_main_runs_on_the_product_library(r1, tmp_path):
+    """the reference's own, unchanged main() (rayweek1.cpp:930-988) compiled against rays1_host.h and
+    linked with librays1_b200.so (oracle/Makefile -> oracle/_ref/rays1_refmain_b200): `-n 1 -w` renders the three scenes at the
+    reference's compiled-in workload and leaves the report blocks, out_<scene>.txt and out_<scene>.tga the reference leaves."""
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "oracle", "_ref", "rays1_refmain_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/rays1_refmain_b200 not built (needs /root/reference at build time)")
+    out = subprocess.run([exe, "-n", "1", "-w"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.splitlines()
+    assert [l for l in lines if l in ("small", "medium", "large")] == ["small", "medium", "large"]
+    assert sum(l == "total samples:  %d" % (1280 * 720 * 250) for l in lines) == 3
+    rays = [int(l.split()[-1]) for l in lines if l.startswith("total rays:")]
+    for got, want in zip(rays, (414.19e6, 577.13e6, 631.16e6)):                    # the reference's own totals (tests/golden/ref_stats.json)
+        assert abs(got / want - 1) < 0.005
+    for name in ("small", "medium", "large"):
+        tok = open(tmp_path / ("out_%s.txt" % name)).read().split("|")
+        assert tok[0] == "latest" and tok[1].endswith("s") and tok[3].endswith(" mrays/s")
+        assert os.path.getsize(tmp_path / ("out_%s.tga" % name)) == 18 + 1280 * 720 * 3
+
+
 def test_in_process_multi_gpu_matches_single_gpu(r1, tmp_path):
     """--gpus 2 in ONE process (NCCL gather + reduce, rays1_host.cpp:render_multi) renders the same bytes and ray count."""
     if r1.device_count() < 2:
@@ -460,7 +482,7 @@ def test_unstaged_global_memory_scan_matches_staged(r1, scenes, monkeypatch):
     s = scenes["large"]
     base, r0 = s.render(160, 90, 24)
     monkeypatch.setenv("R1_FORCE_UNSTAGED", "1")
-    for v in (r1.VARIANT_MEGAKERNEL, r1.VARIANT_MEGAKERNEL_COOP, r1.VARIANT_MEGAKERNEL_SCALAR):
+    for v in (r1.VARIANT_MEGAKERNEL, r1.VARIANT_MEGAKERNEL_COOP, r1.VARIANT_MEGAKERNEL_SCALAR, r1.VARIANT_MEGAKERNEL_DEFERRED):
         alt, ra = s.render(160, 90, 24, variant=v)
         assert np.array_equal(base, alt) and ra.num_rays == r0.num_rays, v
 

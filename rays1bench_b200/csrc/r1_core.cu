@@ -46,6 +46,7 @@ struct Scratch {
     int sm_count = 0, cc_major = 0, cc_minor = 0;
     unsigned long long *accum = nullptr; size_t accum_cap = 0;   // npix_local x 4 fixed-point sums
     unsigned int *unit_counter = nullptr;
+    unsigned long long *sample_counter = nullptr;
     uint8_t *rgb = nullptr; size_t rgb_cap = 0;
     unsigned long long *num_rays = nullptr;
     unsigned long long *host_rays = nullptr;  // pinned
@@ -102,6 +103,7 @@ int get_scratch(int device, Scratch **out)
         R1_CUDA(cudaDeviceGetAttribute(&sc.cc_major, cudaDevAttrComputeCapabilityMajor, device));
         R1_CUDA(cudaDeviceGetAttribute(&sc.cc_minor, cudaDevAttrComputeCapabilityMinor, device));
         R1_CUDA(cudaMalloc(&sc.unit_counter, sizeof(unsigned int)));
+        R1_CUDA(cudaMalloc(&sc.sample_counter, sizeof(unsigned long long)));
         R1_CUDA(cudaMalloc(&sc.num_rays, sizeof(unsigned long long)));
         R1_CUDA(cudaMallocHost(&sc.host_rays, sizeof(unsigned long long)));
         for (auto &e : sc.ev) R1_CUDA(cudaEventCreate(&e));
@@ -162,11 +164,11 @@ Partition partition(int width, int height, int row_tile, int rank, int world)
 constexpr int kDefaultThreads = 1024;     // per-lane scans: 64 registers
 constexpr int kDefaultThreadsCoop = 512;  // cooperative scan: 4 rays per lane in flight, 127 registers
 
-template <int kScan, bool kStaged, int kThreads, bool kRangeAcc>
-int launch_megakernel_tr(int sm_count, const r1::RenderArgs &args, const r1_render_params &prm, cudaStream_t stream)
+template <int kScan, bool kStaged, int kThreads>
+int launch_megakernel_lanefetch(int sm_count, const r1::RenderArgs &args, const r1_render_params &prm, cudaStream_t stream)
 {
     constexpr int kBlocks = 1;
-    auto kern = r1::megakernel<kScan, kStaged, kThreads, kBlocks, kRangeAcc>;
+    auto kern = r1::megakernel<kScan, kStaged, kThreads, kBlocks>;
     const size_t smem = r1::kSmemSpheres + (kStaged ? (size_t)args.scene.n_pad * 32 : 0) + (kScan == r1::kScanCoop || kScan == r1::kScanLaneDeferred ? sizeof(r1::WarpScratch) * (kThreads / 32) : 0);
     R1_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = sm_count * kBlocks;
@@ -179,15 +181,31 @@ int launch_megakernel_tr(int sm_count, const r1::RenderArgs &args, const r1_rend
     return R1_OK;
 }
 
+// warp sample-pool scheduling (r1::megakernel_pool): the default; R1_POOL=0 selects the per-lane unit fetch of r1::megakernel
+template <int kScan, bool kStaged, int kThreads>
+int launch_megakernel_pool(int sm_count, const r1::RenderArgs &args, const r1_render_params &prm, cudaStream_t stream)
+{
+    constexpr int kBlocks = 1;
+    auto kern = r1::megakernel_pool<kScan, kStaged, kThreads, kBlocks>;
+    const size_t smem = r1::kSmemSpheres + (kStaged ? (size_t)args.scene.n_pad * 32 : 0) +
+                        (kScan == r1::kScanCoop || kScan == r1::kScanLaneDeferred ? sizeof(r1::WarpScratch) * (kThreads / 32) : 0) +
+                        sizeof(r1::WarpPool) * (kThreads / 32);
+    R1_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = sm_count * kBlocks;
+    if (prm.blocks_per_sm > 0) grid = sm_count * prm.blocks_per_sm;
+    const unsigned long long max_ctas = (args.n_samples + kThreads - 1) / kThreads;   // never launch more lanes than there are samples
+    if ((unsigned long long)grid > max_ctas) grid = (int)std::max<unsigned long long>(1, max_ctas);
+    kern<<<grid, kThreads, smem, stream>>>(args);
+    R1_CUDA(cudaGetLastError());
+    return R1_OK;
+}
+
 template <int kScan, bool kStaged, int kThreads>
 int launch_megakernel_t(int sm_count, const r1::RenderArgs &args, const r1_render_params &prm, cudaStream_t stream)
 {
-    // register-accumulated ranges only where lanes hold ranges (small scenes) and only for the default scan: the A/B variants
-    // keep the per-sample atomics, which also keeps "one atomic triple per sample" measurable (R1_RANGE_ACC=0 forces it)
-    static const bool allow = !(getenv("R1_RANGE_ACC") && atoi(getenv("R1_RANGE_ACC")) == 0);
-    if (kScan == r1::kScanLanePacked && kThreads == 1024 && args.sched_kmax > 1 && allow)
-        return launch_megakernel_tr<kScan == r1::kScanLanePacked ? kScan : r1::kScanLanePacked, kStaged, kThreads == 1024 ? kThreads : 1024, true>(sm_count, args, prm, stream);
-    return launch_megakernel_tr<kScan, kStaged, kThreads, false>(sm_count, args, prm, stream);
+    const bool pool = !(getenv("R1_POOL") && atoi(getenv("R1_POOL")) == 0);   // read per render, like the other tuning knobs
+    if (pool) return launch_megakernel_pool<kScan, kStaged, kThreads>(sm_count, args, prm, stream);
+    return launch_megakernel_lanefetch<kScan, kStaged, kThreads>(sm_count, args, prm, stream);
 }
 
 template <int kScan, bool kStaged>
@@ -491,6 +509,11 @@ int r1_render_device(r1_scene *scene, const r1_render_params *params, void *d_rg
     a.rgb = (uint8_t *)d_rgb;
     a.num_rays = (unsigned long long *)d_num_rays;
     a.unit_counter = x.unit_counter;
+    a.sample_counter = x.sample_counter;
+    a.n_samples = (uint64_t)a.npix_local * (uint64_t)prm.spp;
+    a.magic_spp = r1::div_magic((uint32_t)prm.spp);
+    // __umul64hi(g, magic_spp) is the exact g / spp for g < 2^64 / spp
+    if ((long double)a.n_samples * (long double)prm.spp >= 18.0e18L) return fail(R1_ERR_LIMIT, "too many samples (%llu x %d spp)", (unsigned long long)a.npix_local, prm.spp);
 
     x.last_launches = 0;
     x.last_wavefront = prm.variant == R1_VARIANT_WAVEFRONT;
@@ -504,6 +527,7 @@ int r1_render_device(r1_scene *scene, const r1_render_params *params, void *d_rg
         a.accum = x.accum;
         R1_CUDA(cudaMemsetAsync(x.accum, 0, (size_t)a.npix_local * 4 * sizeof(unsigned long long), stream));
         R1_CUDA(cudaMemsetAsync(x.unit_counter, 0, sizeof(unsigned int), stream));
+        R1_CUDA(cudaMemsetAsync(x.sample_counter, 0, sizeof(unsigned long long), stream));
         // scenes of up to 4096 spheres are staged in shared memory; R1_FORCE_UNSTAGED=1 exercises the global-memory path on small scenes
         const bool staged = c.dev.n_pad <= r1::kMaxStagedSpheres && !getenv("R1_FORCE_UNSTAGED");
         R1_CUDA(cudaEventRecord(x.ev[1], stream));

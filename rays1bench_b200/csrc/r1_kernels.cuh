@@ -16,8 +16,6 @@ constexpr unsigned kFull = 0xffffffffu;
 // bit-identical for every GPU count, CTA shape, unit size and kernel variant, whatever order the samples arrive in.
 // (The reference sums floats sequentially per pixel, rayweek1.cpp:757-765; radiance per sample is in [0, 1], so 24
 // fractional bits lose < 3e-8 per sample -- float32 itself resolves no better near 1 -- and 2^20 samples fit with room.)
-// Lanes that hold a RANGE of consecutive samples of one pixel (small scenes) first sum up to 32 quantised samples in three
-// 32-bit registers and flush once: integer sums, so the image bytes do not depend on who flushed what when.
 struct RenderArgs {
     DevScene scene;
     unsigned long long *accum;       // npix_local x 4 (r, g, b, -): sum of per-sample radiance * 2^24
@@ -32,12 +30,14 @@ struct RenderArgs {
     uint64_t seed;                   // Rng::seed_hash(global seed)
     uint64_t magic_chunks, magic_width, magic_row_tile;  // floor(2^64 / d) + 1: exact n / d for 32-bit n via one 64-bit mul-high (0 when d == 1)
     uint32_t sched_kmax, sched_div;      // unit ranges: a lane takes min(kmax, max(1, units_left / (lanes * div))) units per fetch
+    // sample-pool scheduling (megakernel_pool): work items are single samples g = lp * spp + s, handed out 32 at a time
+    unsigned long long *sample_counter;  // next sample to hand out (64-bit: 3840 x 2160 x 1024 = 8.5e9 samples)
+    uint64_t n_samples, magic_spp;       // npix_local * spp; floor(2^64 / spp) + 1 (exact g / spp for g < 2^64 / spp; 0 when spp == 1)
 };
 
 constexpr int kSmemSpheres = 16 + R1_RSQRT12_ENTRIES * 2;   // megakernel: byte offset of the staged spheres (mbarrier, rsqrtss table first)
 constexpr float kFixedScale = 16777216.0f;                 // 2^24: one sample (clamped to 4.0) is < 2^26, so 32 samples sum in 32 bits
 constexpr float kFixedInvScale = 5.9604644775390625e-8f;   // 2^-24
-constexpr uint32_t kRangeFlush = 32;                       // register-accumulated samples per flush (range-scheduled scenes)
 
 // n / d for n, d < 2^32 with the precomputed magic (d == 1 -> magic 0)
 __device__ __forceinline__ uint32_t fast_div(uint32_t n, uint64_t magic) { return magic ? (uint32_t)__umul64hi((uint64_t)n, magic) : n; }
@@ -157,10 +157,10 @@ __device__ __forceinline__ bool shade_step(const RenderArgs &a, int hit, float t
 // Replaces render_tile + color + TileRenderScheduler (rayweek1.cpp:722-842, 515-536).
 // kScan: which Hitable::hit implementation the lanes run
 enum ScanKind { kScanCoop = 0, kScanLanePacked = 1, kScanLaneScalar = 2, kScanLaneDeferred = 3 };
+__host__ __device__ constexpr int scan_filter(int kScan) { return kScan == kScanLaneScalar ? 0 : 1; }
 
-// kRangeAcc: lanes sum the samples of their unit range in registers and flush per pixel / per 32 samples (scenes scheduled
-// with ranges, i.e. sched_kmax > 1); false = one atomic triple per sample (scan-heavy scenes, one unit per fetch)
-template <int kScan, bool kStaged, int kThreads, int kBlocksPerSM, bool kRangeAcc = false>
+// (Round-1 scheduling, kept as the A/B alternative of megakernel_pool below: R1_POOL=0.)
+template <int kScan, bool kStaged, int kThreads, int kBlocksPerSM>
 __global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel(const __grid_constant__ RenderArgs a)
 {
     // shared memory: [mbarrier 16 B | rsqrtss table 4 KB | staged spheres n_pad * 32 B | per-warp scratch (cooperative scan)]
@@ -193,7 +193,6 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel(const __gri
     f3 o = mk3(0.0f, 1.0e18f, 0.0f), d = mk3(0.0f, 0.0f, 0.0f);  // idle lanes scan a ray that passes no filter
     Rng rng;
     rng.k0 = 0; rng.k1 = 0;
-    uint32_t acc_r = 0, acc_g = 0, acc_b = 0, acc_n = 0;       // kRangeAcc: quantised radiance of up to kRangeFlush samples of pixel lp
     const uint32_t lanes_x4 = gridDim.x * blockDim.x * a.sched_div;
 
     for (;;) {
@@ -239,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel(const __gri
         int hit = -1;
         if (kScan == kScanCoop) scan_coop<(kThreads <= 512 ? 2 : 1)>(*ws, s_scan, s_exact, n_pad, o, d, kTMin, kTMax, t, hit);
         else if (kScan == kScanLaneDeferred) scan_deferred(*reinterpret_cast<DeferScratch *>(ws), s_scan, s_exact, a.scene.n8, o, d, kTMin, kTMax, t, hit);
-        else scan<kScan == kScanLanePacked>(s_scan, s_exact, a.scene.n8, o, d, kTMin, t, hit);
+        else scan<scan_filter(kScan)>(s_scan, s_exact, a.scene.n8, o, d, kTMin, t, hit);
 
         // -- color() body (rayweek1.cpp:515-536)
         if (active) {
@@ -247,31 +246,196 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel(const __gri
             f3 contrib;
             const float4 e = hit >= 0 ? s_exact[hit] : make_float4(0, 0, 0, 0);
             if (shade_step(a, hit, t, e, tab, o, d, thr, depth, rng, contrib)) {
-                const uint32_t lp_done = lp;
-                bool flush = false;
-                if (kRangeAcc) {
-                    acc_r += quantise_radiance(contrib.x); acc_g += quantise_radiance(contrib.y); acc_b += quantise_radiance(contrib.z);
-                    flush = ++acc_n == kRangeFlush;
-                } else {
-                    accumulate_sample(a, lp, contrib);
-                }
+                accumulate_sample(a, lp, contrib);
                 need_primary = true;
                 if (++s == s_end) {                          // unit done: the next one of my range, or a new range
                     if (++unit == unit_end) {
                         active = false;
-                        flush = true;
                         o = mk3(0.0f, 1.0e18f, 0.0f); d = mk3(0.0f, 0.0f, 0.0f);
                     } else if (s == a.spp) {
-                        flush = true;
                         unit_begin(a, unit, lp, pixel, fx, fy, s, s_end);   // first chunk of the next pixel
                     } else {
                         s_end = min(s + a.samples_per_unit, a.spp);        // next chunk of the same pixel
                     }
                 }
-                if (kRangeAcc && flush) {
-                    accumulate_quantised(a, lp_done, acc_r, acc_g, acc_b);
-                    acc_r = acc_g = acc_b = acc_n = 0;
+            }
+        }
+    }
+    // -- total-rays counter (rayweek1.cpp:809-813): warp reduce, one 64-bit atomic per warp
+    unsigned long long total = nrays;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(kFull, total, off);
+    if (lane == 0 && total) atomicAdd(a.num_rays, total);
+}
+
+// ------------------------------------------------------------------------------------------------ megakernel, warp sample pool
+// The same per-lane path state machine, with the START of a path taken out of the divergent part.  In `megakernel` above a
+// lane that finishes a sample fetches its next unit and generates its primary ray at once, together with whichever other
+// lanes happen to finish in the same iteration: 12 of 32 lanes on the large scene, so the ~300 instructions of fetch + unit
+// decode + RNG seeding + jitter + lens sample + Camera::getRay are paid at 37 % occupancy in every iteration.
+// Here each WARP keeps a pool of up to 32 ready-made primary rays in shared memory.  When the lanes in need outnumber the pool,
+// the whole warp produces the next 32 consecutive samples at once -- one atomicAdd per 32 samples, every lane busy -- and a
+// finishing lane just pops a ray (ballot + popc ranks, three 16-byte loads).  Work items are single samples (no unit ranges:
+// the path state loses unit / sample bookkeeping, eight registers the scan loop can use), numbered g = lp * spp + s in 64 bits.
+// Which lane traces which sample is irrelevant to the result: RNG streams are keyed by (pixel, sample) and the accumulators are
+// integer sums -- the image is bit-identical to the other variants'.
+struct __align__(16) WarpPool {
+    float4 a[32];                     // origin.xyz, local pixel index (uint bits; kPoolInvalid = past the end of the work)
+    float4 b[32];                     // direction.xyz, rng key word 0 (uint bits)
+    uint32_t k1[32];                  // rng key word 1
+};
+constexpr uint32_t kPoolInvalid = 0xffffffffu;
+
+template <int kScan, bool kStaged, int kThreads, int kBlocksPerSM>
+__global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel_pool(const __grid_constant__ RenderArgs a)
+{
+    // shared memory: [mbarrier 16 B | rsqrtss table 4 KB | staged spheres n_pad * 32 B | per-warp scan scratch (coop / deferred) | per-warp pools]
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint16_t *s_tab = reinterpret_cast<uint16_t *>(smem_raw + 16);
+    for (int i = threadIdx.x; i < R1_RSQRT12_ENTRIES / 2; i += kThreads)
+        reinterpret_cast<uint32_t *>(s_tab)[i] = reinterpret_cast<const uint32_t *>(g_rsqrt12)[i];
+    const float4 *s_scan, *s_exact;
+    if (kStaged) {
+        float4 *s_spheres = reinterpret_cast<float4 *>(smem_raw + kSmemSpheres);
+        stage_spheres(a.scene, s_spheres, reinterpret_cast<uint64_t *>(smem_raw));   // its __syncthreads also publishes the table
+        s_scan = s_spheres;
+        s_exact = s_spheres + a.scene.n_pad;
+    } else {  // scenes beyond the staging limit scan straight from global memory (L1/L2 resident)
+        s_scan = a.scene.scan;
+        s_exact = a.scene.exact;
+        __syncthreads();
+    }
+    const uint16_t *tab = s_tab;
+    const int n_pad = a.scene.n_pad;
+    const unsigned lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
+    constexpr bool kScratch = kScan == kScanCoop || kScan == kScanLaneDeferred;
+    unsigned char *after_spheres = smem_raw + kSmemSpheres + (kStaged ? (size_t)n_pad * 32 : 0);
+    WarpScratch *ws = reinterpret_cast<WarpScratch *>(after_spheres) + (threadIdx.x >> 5);
+    WarpPool &pool = reinterpret_cast<WarpPool *>(after_spheres + (kScratch ? sizeof(WarpScratch) * (kThreads / 32) : 0))[threadIdx.x >> 5];
+
+    bool active = false, exhausted = false;
+    bool dry = false;                                            // warp-uniform: the sample counter has run past the end
+    uint32_t ready = 0;                                          // warp-uniform: rays in the pool, entries [0, ready)
+    // warp-uniform: the warp's private range of samples [w_next, w_end).  Scan-heavy scenes take 32 samples per atomic; small
+    // scenes, where a scan is a few hundred instructions and one atomic per 32 samples would saturate the counter's L2 line,
+    // take up to sched_kmax x 32, shrinking as left / (sched_div x lanes) so that the last warps finish together.
+    unsigned long long w_next = 0, w_end = 0;
+    const uint32_t lanes_x = gridDim.x * blockDim.x * a.sched_div;
+    uint32_t lp = 0, nrays = 0;
+    int depth = 0;
+    f3 thr = mk3(1, 1, 1);
+    f3 o = mk3(0.0f, 1.0e18f, 0.0f), d = mk3(0.0f, 0.0f, 0.0f);  // idle lanes scan a ray that passes no filter
+    Rng rng;
+    rng.k0 = 0; rng.k1 = 0;
+
+    for (;;) {
+        // -- lanes without a path take a ray from the warp's pool; the warp refills the pool when it runs short
+        const bool want = !active && !exhausted;
+        const unsigned need = __ballot_sync(kFull, want);
+        if (need) {
+            const uint32_t n_need = (uint32_t)__popc(need), rank = (uint32_t)__popc(need & lt_mask);
+            int entry = -1;                                      // pool entry this lane pops
+            if (want && rank < ready) entry = (int)(ready - 1u - rank);
+            const uint32_t n_first = min(n_need, ready);
+            if (n_need > ready && !dry) {                        // warp-uniform: not enough rays, produce the next 32 samples
+                float4 ea = make_float4(0, 0, 0, 0), eb = make_float4(0, 0, 0, 0);
+                uint32_t ek1 = 0;
+                if (entry >= 0) { ea = pool.a[entry]; eb = pool.b[entry]; ek1 = pool.k1[entry]; }   // pop before the pool is overwritten
+                __syncwarp();
+                if (w_next >= w_end) {                           // the private range is used up: take the next one
+                    unsigned long long base = 0;
+                    uint32_t k = 1;
+                    if (lane == 0) {
+                        const unsigned long long left = a.n_samples > w_end ? a.n_samples - w_end : 0ull;
+                        const unsigned long long want_k = left / lanes_x;
+                        k = want_k >= a.sched_kmax ? a.sched_kmax : (want_k < 1 ? 1u : (uint32_t)want_k);
+                        base = atomicAdd(a.sample_counter, 32ull * k);
+                    }
+                    base = __shfl_sync(kFull, base, 0);
+                    k = __shfl_sync(kFull, k, 0);
+                    w_next = base;
+                    w_end = base + 32ull * k < a.n_samples ? base + 32ull * k : a.n_samples;
                 }
+                if (w_next >= a.n_samples) {
+                    dry = true;
+                    ready = 0;
+                } else {
+                    const unsigned long long g = w_next + lane;
+                    w_next += 32;
+                    float4 pa = make_float4(0, 0, 0, __uint_as_float(kPoolInvalid)), pb = make_float4(0, 0, 0, 0);
+                    uint32_t pk1 = 0;
+                    if (g < a.n_samples) {
+                        // sample g -> (local pixel, sample index) -> global pixel under the interleaved row-tile partition
+                        const uint32_t plp = a.magic_spp ? (uint32_t)__umul64hi(g, a.magic_spp) : (uint32_t)g;
+                        const uint32_t smp = (uint32_t)(g - (unsigned long long)plp * (uint32_t)a.spp);
+                        const uint32_t lr = fast_div(plp, a.magic_width);
+                        const int x = (int)(plp - lr * (uint32_t)a.width);
+                        const uint32_t tile = fast_div(lr, a.magic_row_tile);
+                        const int y = (int)((tile * (uint32_t)a.world + (uint32_t)a.rank) * (uint32_t)a.row_tile + (lr - tile * (uint32_t)a.row_tile));
+                        Rng r;
+                        f3 po, pd;
+                        primary_ray(a, (uint32_t)y * (uint32_t)a.width + (uint32_t)x, (float)x, (float)y, (int)smp, tab, r, po, pd);
+                        pa = make_float4(po.x, po.y, po.z, __uint_as_float(plp));
+                        pb = make_float4(pd.x, pd.y, pd.z, __uint_as_float(r.k0));
+                        pk1 = r.k1;
+                    }
+                    pool.a[lane] = pa; pool.b[lane] = pb; pool.k1[lane] = pk1;
+                    ready = 32;
+                }
+                __syncwarp();
+                const uint32_t rank2 = rank - n_first;           // rank among the lanes the old pool could not serve
+                if (want && entry < 0 && rank2 < ready) {
+                    entry = (int)(ready - 1u - rank2);
+                    ea = pool.a[entry]; eb = pool.b[entry]; ek1 = pool.k1[entry];
+                }
+                ready -= min(n_need - n_first, ready);
+                if (want) {
+                    if (entry >= 0 && __float_as_uint(ea.w) != kPoolInvalid) {
+                        o = mk3(ea.x, ea.y, ea.z); d = mk3(eb.x, eb.y, eb.z); lp = __float_as_uint(ea.w);
+                        rng.k0 = __float_as_uint(eb.w); rng.k1 = ek1;
+                        thr = mk3(1, 1, 1); depth = 0; active = true;
+                    } else {
+                        exhausted = true;                        // past the end of the work
+                        o = mk3(0.0f, 1.0e18f, 0.0f); d = mk3(0.0f, 0.0f, 0.0f);
+                    }
+                }
+            } else {                                             // the pool serves everybody (or there is nothing left to produce)
+                ready -= n_first;
+                if (want) {
+                    bool got = false;
+                    if (entry >= 0) {
+                        const float4 ea = pool.a[entry], eb = pool.b[entry];
+                        if (__float_as_uint(ea.w) != kPoolInvalid) {
+                            o = mk3(ea.x, ea.y, ea.z); d = mk3(eb.x, eb.y, eb.z); lp = __float_as_uint(ea.w);
+                            rng.k0 = __float_as_uint(eb.w); rng.k1 = pool.k1[entry];
+                            thr = mk3(1, 1, 1); depth = 0; active = true; got = true;
+                        }
+                    }
+                    if (!got) {
+                        exhausted = true;
+                        o = mk3(0.0f, 1.0e18f, 0.0f); d = mk3(0.0f, 0.0f, 0.0f);
+                    }
+                }
+            }
+        }
+        if (__all_sync(kFull, exhausted)) break;
+
+        // -- Hitable::hit (rayweek1.cpp:152-339): uniform trip count, all lanes
+        float t = kTMax;
+        int hit = -1;
+        if (kScan == kScanCoop) scan_coop<(kThreads <= 512 ? 2 : 1)>(*ws, s_scan, s_exact, n_pad, o, d, kTMin, kTMax, t, hit);
+        else if (kScan == kScanLaneDeferred) scan_deferred(*reinterpret_cast<DeferScratch *>(ws), s_scan, s_exact, a.scene.n8, o, d, kTMin, kTMax, t, hit);
+        else scan<scan_filter(kScan)>(s_scan, s_exact, a.scene.n8, o, d, kTMin, t, hit);
+
+        // -- color() body (rayweek1.cpp:515-536)
+        if (active) {
+            ++nrays;
+            f3 contrib;
+            const float4 e = hit >= 0 ? s_exact[hit] : make_float4(0, 0, 0, 0);
+            if (shade_step(a, hit, t, e, tab, o, d, thr, depth, rng, contrib)) {
+                accumulate_sample(a, lp, contrib);
+                active = false;
+                o = mk3(0.0f, 1.0e18f, 0.0f); d = mk3(0.0f, 0.0f, 0.0f);    // (overwritten by the pop at the top of the loop)
             }
         }
     }
@@ -330,7 +494,7 @@ __global__ void __launch_bounds__(128) trace_rays_kernel(const __grid_constant__
     int hit = -1;
     if (kScan == kScanCoop) scan_coop<2>(*ws, s_spheres, s_spheres + sc.n_pad, sc.n_pad, o, d, t_min, t_max, t, hit);
     else if (kScan == kScanLaneDeferred) scan_deferred(*reinterpret_cast<DeferScratch *>(ws), s_spheres, s_spheres + sc.n_pad, sc.n8, o, d, t_min, t_max, t, hit);
-    else scan<kScan == kScanLanePacked>(s_spheres, s_spheres + sc.n_pad, sc.n8, o, d, t_min, t, hit);
+    else scan<scan_filter(kScan)>(s_spheres, s_spheres + sc.n_pad, sc.n8, o, d, t_min, t, hit);
     if (!live) return;
     f3 p = mk3(0, 0, 0), nrm = mk3(0, 0, 0);
     if (hit >= 0) hit_finalise(s_spheres[sc.n_pad + hit], load_shade(sc, hit).inv_radius, o, d, t, p, nrm);
@@ -431,7 +595,7 @@ __global__ void __launch_bounds__(128) replay_pixels_kernel(const __grid_constan
             ++rays;
             float t = kTMax;
             int hit = -1;
-            scan<true>(s_scan, s_exact, sc.n8, o, d, kTMin, t, hit);
+            scan<1>(s_scan, s_exact, sc.n8, o, d, kTMin, t, hit);
             if (hit < 0) { leaf = sky(d); break; }
             if (depth >= max_bounces) break;
             f3 p, nrm, atten, nd, rs = mk3(0, 0, 0);

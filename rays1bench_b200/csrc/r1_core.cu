@@ -493,14 +493,14 @@ int r1_render_device(r1_scene *scene, const r1_render_params *params, void *d_rg
     a.magic_chunks = r1::div_magic((uint32_t)a.n_chunks);
     a.magic_width = r1::div_magic((uint32_t)prm.width);
     a.magic_row_tile = r1::div_magic((uint32_t)prm.row_tile);
-    // Units per fetch (guided self-scheduling, r1::megakernel).  Measured on B200, Mrays/s full image | 1/8 image (the 8-GPU
-    // partition):            1 unit per fetch        up to 64, shrinking as left / (16 * lanes)      up to 16, left / (4 * lanes)
-    //   large  (488)          5875 | 5870             5879 | 5805                                      5861 | 5437
-    //   medium (48)          23724 | 23210           27411 | 25229                                    26928 | 23044
-    //   small  (8)           27367 | 27579           45336 | 37358                                    43391 | 37023
-    // Ranges held by lanes at the end of a render are a serial tail; single units make one atomic per warp per bounce,
-    // which saturates the counter's L2 line when a scan is only a few hundred instructions.
-    if (c.dev.n8 >= 256) { a.sched_kmax = 1; a.sched_div = 1; }
+    // Samples per atomic (guided self-scheduling).  r1::megakernel_pool: a WARP takes kmax x 32 consecutive samples per atomicAdd,
+    // shrinking as left / (div x lanes) towards the end.  Measured on B200 (large scene, Mrays/s, full image | rank 0 of 8 = the
+    // per-GPU share of the 8-GPU partition):  1,1: 6066 | 6057   2,16: 6102 | 6088   4,16: 6121 | 6088   8,16: 6132 | 6103.
+    // Small scenes need long ranges: with 32 samples per atomic the one counter line in L2 saturates (small scene 39 G rays/s
+    // instead of 58).  r1::megakernel (R1_POOL=0) hands units to LANES; its round-1 tuning is kept: 1 unit per fetch on
+    // scan-heavy scenes (ranges held by lanes at the end of a render are a serial tail), up to 64 on small ones.
+    const bool pool_sched = !(getenv("R1_POOL") && atoi(getenv("R1_POOL")) == 0);
+    if (c.dev.n8 >= 256) { a.sched_kmax = pool_sched ? 8 : 1; a.sched_div = pool_sched ? 16 : 1; }
     else { a.sched_kmax = 64; a.sched_div = 16; }
     if (const char *e = getenv("R1_SCHED")) {  // tuning knob: "kmax,div"
         unsigned k = 0, d = 0;

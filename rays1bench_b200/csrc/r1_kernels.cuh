@@ -142,9 +142,12 @@ __device__ __forceinline__ bool shade_step(const RenderArgs &a, int hit, float t
     hit_finalise(e, sh.inv_radius, o, d, t, p, n);
     const int kind = sh.kind;
     const float4 mat = sh.mat;
+    // One code path for every material: draw 0 of this bounce is Dielectric's coin AND the radius variable of the unit-ball
+    // sample Lambertian / Metal use (a dielectric hit throws its ball sample away).  Branching on the material first made the
+    // warp run the ~50 instructions of the ball sample once per material present in it.
     const uint32_t draw0 = kDrawsPrimary + kDrawsPerBounce * (uint32_t)depth;
-    if (kind == 2) ru = rng.rand01(draw0);
-    else rs = random_in_unit_sphere(rng, draw0);
+    ru = rng.rand01(draw0);
+    rs = random_in_unit_sphere(rng, draw0, ru);
     if (!scatter(kind, mat, d, p, n, rs, ru, tab, atten, nd)) return true;
     thr = mk3(fmul(thr.x, atten.x), fmul(thr.y, atten.y), fmul(thr.z, atten.z));
     o = p; d = nd; ++depth;

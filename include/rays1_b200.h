@@ -119,6 +119,9 @@ int r1_render_device(r1_scene *scene, const r1_render_params *params, void *d_rg
 /* Blocks until the last r1_render_device of this scene on `device` (< 0: device of the last commit) has finished and
  * fills kernel_ms / trace_ms (CUDA events recorded on the launching stream), launches, n_units, num_samples. */
 int r1_render_wait(r1_scene *scene, int device, r1_result *result);
+/* Diagnostics: how many times the wavefront variant had to (re)build its CUDA-graph WHILE loop on `device` -- the
+ * instantiated graph is cached and re-launched while the render arguments stay the same.  Negative on error. */
+int r1_wavefront_graph_builds(int device);
 /* Rows / pixels owned by `rank` under the interleaved row-tile partition, and the global row of local row `lr`. */
 int64_t r1_local_rows(int height, int row_tile, int rank, int world);
 int64_t r1_local_pixels(int width, int height, int row_tile, int rank, int world);

@@ -71,6 +71,7 @@ def _load():
         "r1_render": (ci, [vp, C.POINTER(RenderParams), u8p, C.POINTER(Result)]),
         "r1_render_device": (ci, [vp, C.POINTER(RenderParams), vp, vp, vp, C.POINTER(Result)]),
         "r1_render_wait": (ci, [vp, ci, C.POINTER(Result)]),
+        "r1_wavefront_graph_builds": (ci, [ci]),
         "r1_local_rows": (C.c_int64, [ci, ci, ci, ci]),
         "r1_local_pixels": (C.c_int64, [ci, ci, ci, ci, ci]),
         "r1_global_row": (ci, [ci, ci, ci, ci]),

@@ -596,6 +596,14 @@ int r1_render_wait(r1_scene *scene, int device, r1_result *result)
     return R1_OK;
 }
 
+int r1_wavefront_graph_builds(int device)
+{
+    Scratch *xp = nullptr;
+    int rc = get_scratch(device, &xp);
+    if (rc) return rc;
+    return (int)xp->wf.graph_builds;
+}
+
 int r1_render(r1_scene *scene, const r1_render_params *params, uint8_t *rgb_host, r1_result *result)
 {
     const auto t0 = std::chrono::steady_clock::now();

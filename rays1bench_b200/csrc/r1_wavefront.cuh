@@ -13,6 +13,7 @@
 // Finished samples go to the same fixed-point pixel accumulators as the megakernel's, so both variants produce
 // bit-identical images.  State: one 64-byte record per slot, ~2.4 M slots.
 #pragma once
+#include <cstring>
 #include "r1_kernels.cuh"
 
 #include <cstdio>
@@ -38,10 +39,20 @@ struct WfState {
     uint32_t n_slots;
 };
 
+// what an instantiated loop graph was captured with: it can be launched again as long as none of this changed
+struct WfGraphKey {
+    RenderArgs a;
+    WfState w;
+    void (*ikern)(RenderArgs, WfState);
+    int igrid, ithreads, sgrid;
+    size_t smem;
+};
 struct WavefrontBuffers {
     void *pool = nullptr;
     size_t pool_bytes = 0;
-    cudaGraphExec_t exec = nullptr;
+    cudaGraphExec_t exec = nullptr;    // instantiated WHILE-loop graph, cached across renders
+    WfGraphKey key;                    // valid while exec != nullptr
+    uint32_t graph_builds = 0;         // how many times the graph had to be (re)built (diagnostics / tests)
     uint32_t *d_iterations = nullptr;  // device counter of loop iterations of the last render
 };
 
@@ -258,6 +269,7 @@ inline int wavefront_render(WavefrontBuffers &b, const RenderArgs &a, int sm_cou
 {
     *launches = 0;
     WfState w;
+    memset(&w, 0, sizeof(w));   // padding too: the graph cache compares the struct bytewise
     w.n_slots = wavefront_slots(a.n_units, sm_count);
     const size_t n = w.n_slots;
     const size_t bytes = n * (64 + 16 + 8) + 64 + 256;
@@ -328,33 +340,42 @@ inline int wavefront_render(WavefrontBuffers &b, const RenderArgs &a, int sm_cou
         b.d_iterations = nullptr;
         return 0;
     }
-    // the loop as a CUDA-graph WHILE node: intersect -> shade -> decide, repeated on the device until no slot is alive
-    if (b.exec) {  // the previous render's graph may still be running on this stream
-        R1_WF_CUDA(cudaStreamSynchronize(stream));
+    // the loop as a CUDA-graph WHILE node: intersect -> shade -> decide, repeated on the device until no slot is alive.
+    // Kernel arguments are baked into the instantiated graph, so it is cached and re-launched while they stay the same
+    // (every render of a benchmark loop); any change -- another scene block, image size, buffers, kernel configuration -- rebuilds it.
+    WfGraphKey key;
+    memset(&key, 0, sizeof(key));
+    key.a = a; key.w = w; key.ikern = ikern; key.igrid = igrid; key.ithreads = cfg_t; key.sgrid = sgrid; key.smem = smem;
+    if (b.exec && memcmp(&key, &b.key, sizeof(key)) != 0) {
+        R1_WF_CUDA(cudaStreamSynchronize(stream));   // the previous render's graph may still be running on this stream
         cudaGraphExecDestroy(b.exec);
         b.exec = nullptr;
     }
-    cudaGraph_t graph = nullptr;
-    R1_WF_CUDA(cudaGraphCreate(&graph, 0));
-    cudaGraphConditionalHandle handle;
-    R1_WF_CUDA(cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault));
-    cudaGraphNodeParams cond = { cudaGraphNodeTypeConditional };
-    cond.conditional.handle = handle;
-    cond.conditional.type = cudaGraphCondTypeWhile;
-    cond.conditional.size = 1;
-    cudaGraphNode_t node;
-    R1_WF_CUDA(cudaGraphAddNode(&node, graph, nullptr, 0, &cond));
-    cudaGraph_t body = cond.conditional.phGraph_out[0];
-    cudaStream_t cap;
-    R1_WF_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
-    R1_WF_CUDA(cudaStreamBeginCaptureToGraph(cap, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
-    ikern<<<igrid, cfg_t, smem, cap>>>(a, w);
-    wf_shade<<<sgrid, 256, 0, cap>>>(a, w);
-    wf_decide<<<1, 1, 0, cap>>>(w, handle, nullptr);
-    R1_WF_CUDA(cudaStreamEndCapture(cap, nullptr));
-    R1_WF_CUDA(cudaStreamDestroy(cap));
-    R1_WF_CUDA(cudaGraphInstantiate(&b.exec, graph, 0));
-    R1_WF_CUDA(cudaGraphDestroy(graph));
+    if (!b.exec) {
+        cudaGraph_t graph = nullptr;
+        R1_WF_CUDA(cudaGraphCreate(&graph, 0));
+        cudaGraphConditionalHandle handle;
+        R1_WF_CUDA(cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault));
+        cudaGraphNodeParams cond = { cudaGraphNodeTypeConditional };
+        cond.conditional.handle = handle;
+        cond.conditional.type = cudaGraphCondTypeWhile;
+        cond.conditional.size = 1;
+        cudaGraphNode_t node;
+        R1_WF_CUDA(cudaGraphAddNode(&node, graph, nullptr, 0, &cond));
+        cudaGraph_t body = cond.conditional.phGraph_out[0];
+        cudaStream_t cap;
+        R1_WF_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+        R1_WF_CUDA(cudaStreamBeginCaptureToGraph(cap, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+        ikern<<<igrid, cfg_t, smem, cap>>>(a, w);
+        wf_shade<<<sgrid, 256, 0, cap>>>(a, w);
+        wf_decide<<<1, 1, 0, cap>>>(w, handle, nullptr);
+        R1_WF_CUDA(cudaStreamEndCapture(cap, nullptr));
+        R1_WF_CUDA(cudaStreamDestroy(cap));
+        R1_WF_CUDA(cudaGraphInstantiate(&b.exec, graph, 0));
+        R1_WF_CUDA(cudaGraphDestroy(graph));
+        b.key = key;
+        ++b.graph_builds;
+    }
     R1_WF_CUDA(cudaGraphLaunch(b.exec, stream));
     // 3 kernels per loop iteration; the iteration count lives on the device (d_iterations) and is read by r1_render_wait
     *launches += 0;

@@ -336,3 +336,13 @@ def test_reference_main_compiles_unchanged_against_the_host_header(r1):
     if n == 0:
         out = subprocess.run([ref_main, "-n", "1"], capture_output=True, text=True, timeout=120)
         assert out.returncode == 1 and "rays1_b200: create_small_scene" in out.stderr, "no device -> fatal, never a CPU render"
+
+
+def test_bench_steps_tool_compiles_the_executable(r1):
+    """tools/bench_steps.py (the reference's bench.py driver for this build): --compile-only builds the
+    in-tree executable with nvcc and stops, like the reference's --compile-only (bench.py:100-104 there)"""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_steps.py"), "--latest", "--compile-only"],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.strip().splitlines()[-1] == "compiled " + r1.EXE_PATH
+    assert os.access(r1.EXE_PATH, os.X_OK) and "RUN " not in out.stdout

@@ -322,6 +322,37 @@ def test_wavefront_full_size_matches_megakernel(r1, scenes, name):
     assert np.array_equal(part, a[rows])
 
 
+def test_wavefront_graph_is_cached_across_renders(r1, scenes):
+    """the wavefront's CUDA-graph WHILE loop is instantiated once and re-launched while the render arguments stay the same"""
+    s = scenes["medium"]
+    a, ra = s.render(160, 90, 8, variant=r1.VARIANT_WAVEFRONT)
+    n0 = r1.lib.r1_wavefront_graph_builds(0)
+    for _ in range(3):
+        b, rb = s.render(160, 90, 8, variant=r1.VARIANT_WAVEFRONT)
+        assert np.array_equal(a, b) and ra.num_rays == rb.num_rays
+    assert r1.lib.r1_wavefront_graph_builds(0) == n0, "same arguments: no rebuild"
+    c, rc = s.render(160, 90, 9, variant=r1.VARIANT_WAVEFRONT)
+    assert r1.lib.r1_wavefront_graph_builds(0) == n0 + 1, "another spp: rebuilt once"
+    ref, rr = s.render(160, 90, 9)
+    assert np.array_equal(c, ref) and rc.num_rays == rr.num_rays
+
+
+def test_sample_pool_and_lane_fetch_scheduling_render_the_same_bytes(r1, scenes, monkeypatch):
+    """r1::megakernel_pool (default: warps produce 32 primary rays at a time, finishing lanes pop them) against r1::megakernel
+    (round-1 scheduling: every lane fetches and generates its own next sample, R1_POOL=0), incl. ragged sizes and partitions"""
+    for name, (w, h, spp) in (("large", (200, 117, 40)), ("small", (33, 7, 3)), ("synth4096", (64, 36, 5))):
+        s = scenes[name]
+        monkeypatch.delenv("R1_POOL", raising=False)
+        a, ra = s.render(w, h, spp)
+        a2, ra2 = s.render(w, h, spp, rank=1, world=3)
+        monkeypatch.setenv("R1_POOL", "0")
+        b, rb = s.render(w, h, spp)
+        b2, rb2 = s.render(w, h, spp, rank=1, world=3)
+        assert np.array_equal(a, b) and ra.num_rays == rb.num_rays and ra.num_samples == rb.num_samples == w * h * spp
+        assert np.array_equal(a2, b2) and ra2.num_rays == rb2.num_rays
+    monkeypatch.delenv("R1_POOL", raising=False)
+
+
 # ---- determinism / partition invariance --------------------------------------------------------------------------------
 
 def test_bitwise_invariance(r1, scenes):
@@ -415,6 +446,19 @@ def test_drop_in_executable(r1, tmp_path):
         tok = txt.split("|")
         assert tok[0] == "b200" and tok[1].endswith("s") and int(tok[2]) > 1280 * 720 * 4 and tok[3].endswith(" mrays/s") and tok[4] == ""
         assert os.path.getsize(tmp_path / ("out_%s.tga" % name)) == 18 + 1280 * 720 * 3
+
+
+def test_bench_steps_tool_runs_the_executable(r1, tmp_path):
+    """tools/bench_steps.py --quick --num 2 --save: the reference's driver flow (compile, run with -n / -w, collect out_<scene>.txt)"""
+    import sys
+    from conftest import ROOT
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_steps.py"), "--latest", "--quick", "--num", "2", "--save", "--outdir",
+                          str(tmp_path)], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.count("total samples:  %d" % (80 * 60 * 100)) == 6          # 3 scenes x 2 runs at the QUICKBENCH size (common.h:3-16)
+    for name in ("small", "medium", "large"):
+        assert open(tmp_path / ("out_%s.txt" % name)).read().startswith("b200|")
+        assert os.path.getsize(tmp_path / ("out_%s.tga" % name)) == 18 + 80 * 60 * 3
 
 
 def test_reference_main_runs_on_the_product_library(r1, tmp_path):

@@ -26,7 +26,11 @@ def main():
     ap.add_argument("--compile-only", action="store_true")
     ap.add_argument("--outdir", default=os.path.join(ROOT, "rays1bench_b200"))
     args = ap.parse_args()
-    from rays1bench_b200 import build as b
+    # rays1bench_b200/build.py is loaded by path: importing the package needs the library this step builds
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("rays1bench_b200_build", os.path.join(ROOT, "rays1bench_b200", "build.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
     lib, exe = b.build()
     print("compiled", exe)
     if args.compile_only:

@@ -84,9 +84,9 @@ void r1_scene_destroy(r1_scene *scene);
 /* Camera::init (rayweek1.cpp:366-379). */
 int r1_scene_set_camera(r1_scene *scene, const float lookfrom[3], const float lookat[3], const float vup[3], float vfov_deg,
                         float aspect, float aperture, float focus_dist);
-/* Installs the 22 camera constants directly, in the order r1_scene_get_camera returns them.  For callers that already hold
- * the reference's own constants (its Camera::init is folded at compile time by gcc -ffast-math and differs from the run-time
- * evaluation above by up to 4 ulp): the per-pixel replay fixtures of tests/golden use it to reproduce primary rays bit for bit. */
+/* Installs the 22 camera constants directly, in the order r1_scene_get_camera returns them -- for callers that already hold
+ * camera constants of their own (r1_scene_set_camera itself reproduces the reference's constants bit for bit: it evaluates
+ * Camera::init the way gcc -ffast-math folds it for the reference's builders). */
 int r1_scene_set_camera_raw(r1_scene *scene, const float cam[22]);
 /* SphereSOA::add (soa_sphere.cpp:70-85): stores radius*radius and radius > 0 ? 1/radius : 0.  Metal's `param` is the
  * fuzz (clamped to <= 1 as the Metal ctor does, rayweek1.cpp:424), Dielectric's the refraction index.  Returns the

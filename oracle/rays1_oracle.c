@@ -208,13 +208,28 @@ static void scene_pad(orc_scene *s, uint32_t multiple)
 /* rayweek1.cpp:366-379 -- Camera::init */
 static void camera_init(orc_scene *s, v3 lookfrom, v3 lookat, v3 vup, float vfov, float aspect, float aperture, float focus_dist)
 {
+    /* The builders call Camera::init with constants, so gcc folds it at COMPILE time -- with the fast-math reassociations applied
+     * first: `vfov * (float)M_PI / 180 / 2` becomes vfov * C with C = (float)M_PI * (1.0f / 360.0f), the functions (tanf, the
+     * 1 / sqrtf of unit_vector) are then evaluated correctly rounded, everything else in source order.  Checked bit for bit against
+     * the constants recorded from the reference's binary for all four scenes (tests/golden/rays_*.npz "camera").  With
+     * g_as_built = 0: the source order, theta = vfov * pi / 180, tanf(theta / 2). */
     s->lens_radius = aperture / 2;
-    float theta = vfov * (float)M_PI / 180;
-    float half_height = tanf(theta / 2);
+    float half_height;
+    if (g_as_built) {
+        const float c = (float)M_PI * (1.0f / 360.0f);
+        half_height = (float)tan((double)(vfov * c));
+    } else {
+        float theta = vfov * (float)M_PI / 180;
+        half_height = tanf(theta / 2);
+    }
     float half_width = aspect * half_height;
     s->origin = lookfrom;
-    s->w = v3_unit(v3_sub(lookfrom, lookat));
-    s->u = v3_unit(v3_cross(vup, s->w));
+    {   /* unit_vector folded at compile time: the exact 1 / sqrt, not the run-time rsqrtss + Newton step */
+        v3 a = v3_sub(lookfrom, lookat);
+        s->w = v3_scale(a, 1.0f / sqrtf(v3_dot(a, a)));
+        v3 b = v3_cross(vup, s->w);
+        s->u = v3_scale(b, 1.0f / sqrtf(v3_dot(b, b)));
+    }
     s->v = v3_cross(s->w, s->u);
     s->llc = v3_sub(v3_sub(v3_sub(s->origin, v3_scale(s->u, half_width * focus_dist)),
                            v3_scale(s->v, half_height * focus_dist)),

@@ -268,9 +268,13 @@ int r1_scene_set_camera(r1_scene *scene, const float lookfrom[3], const float lo
 {
     if (!scene || !lookfrom || !lookat || !vup) return fail(R1_ERR_ARG, "null argument");
     r1::Camera &c = scene->cam;
+    // The reference's builders call Camera::init with constants, so gcc folds it at compile time -- after the fast-math
+    // reassociation of `vfov * (float)M_PI / 180 / 2` into vfov * C, C = (float)M_PI * (1.0f / 360.0f) -- with tanf and the 1 / sqrtf
+    // of unit_vector correctly rounded and everything else in source order.  Evaluated the same way here, the 22 constants have the
+    // reference's exact bits for its three scenes (checked against the constants recorded from its binary, tests/test_abi_cpu.py).
     c.lens_radius = aperture / 2;
-    const float theta = vfov_deg * (float)M_PI / 180;
-    const float half_height = tanf(theta / 2);
+    const float half_angle_per_degree = (float)M_PI * (1.0f / 360.0f);
+    const float half_height = (float)tan((double)(vfov_deg * half_angle_per_degree));
     const float half_width = aspect * half_height;
     for (int k = 0; k < 3; ++k) { c.origin[k] = lookfrom[k]; c.w[k] = lookfrom[k] - lookat[k]; }
     v3_unit(c.w);
@@ -406,9 +410,14 @@ int r1_scene_commit(r1_scene *scene, int device)
             inv_r = scene->inv_radius[i];
             kind = scene->kind[i];
         }
-        float kind_bits;
+        float kind_bits, inv_ior = 0.0f, r0s = 0.0f;
         memcpy(&kind_bits, &kind, 4);
-        shade[2 * i + 1] = make_float4(inv_r, kind_bits, 0.0f, 0.0f);
+        if (kind == R1_MAT_DIELECTRIC) {   // Dielectric::scatter's two divisions (rayweek1.cpp:482, :456), once per sphere, IEEE float
+            const volatile float ior = scene->param[i];
+            inv_ior = 1.0f / ior;
+            r0s = (1.0f - ior) / (ior + 1.0f);
+        }
+        shade[2 * i + 1] = make_float4(inv_r, kind_bits, inv_ior, r0s);
     }
     R1_CUDA(cudaMalloc(&c.block, bytes));
     {

@@ -148,7 +148,7 @@ __device__ __forceinline__ bool shade_step(const RenderArgs &a, int hit, float t
     const uint32_t draw0 = kDrawsPrimary + kDrawsPerBounce * (uint32_t)depth;
     ru = rng.rand01(draw0);
     rs = random_in_unit_sphere(rng, draw0, ru);
-    if (!scatter(kind, mat, d, p, n, rs, ru, tab, atten, nd)) return true;
+    if (!scatter(kind, mat, sh.inv_ior, sh.r0s, d, p, n, rs, ru, tab, atten, nd)) return true;
     thr = mk3(fmul(thr.x, atten.x), fmul(thr.y, atten.y), fmul(thr.z, atten.z));
     o = p; d = nd; ++depth;
     return false;
@@ -517,7 +517,7 @@ __global__ void scatter_kernel(const __grid_constant__ DevScene sc, int n, const
     bool r = false;
     const ShadeRec sh = load_shade(sc, i >= 0 && i < sc.n_pad ? i : 0);
     if (i >= 0 && i < sc.n_pad && sh.kind >= 0)
-        r = scatter(sh.kind, sh.mat, mk3(dir_in[3 * k], dir_in[3 * k + 1], dir_in[3 * k + 2]), mk3(p[3 * k], p[3 * k + 1], p[3 * k + 2]),
+        r = scatter(sh.kind, sh.mat, sh.inv_ior, sh.r0s, mk3(dir_in[3 * k], dir_in[3 * k + 1], dir_in[3 * k + 2]), mk3(p[3 * k], p[3 * k + 1], p[3 * k + 2]),
                     mk3(nrm[3 * k], nrm[3 * k + 1], nrm[3 * k + 2]), mk3(rs[3 * k], rs[3 * k + 1], rs[3 * k + 2]), ru[k], g_rsqrt12, a, dd);
     ok[k] = r ? 1 : 0;
     atten[3 * k] = a.x; atten[3 * k + 1] = a.y; atten[3 * k + 2] = a.z;
@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(128) replay_pixels_kernel(const __grid_constan
                     rs = mk3(fsub(r4[0], 1.0f), fsub(r4[1], 1.0f), fsub(r4[2], 1.0f));
                 } while (fadd(fadd(fmul(rs.x, rs.x), fmul(rs.y, rs.y)), fmul(rs.z, rs.z)) >= 1.0f);
             }
-            if (!scatter(kind, sh.mat, d, p, nrm, rs, ru, g_rsqrt12, atten, nd)) break;
+            if (!scatter(kind, sh.mat, sh.inv_ior, sh.r0s, d, p, nrm, rs, ru, g_rsqrt12, atten, nd)) break;
             stack[depth++] = atten;
             o = p; d = nd;
         }

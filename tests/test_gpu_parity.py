@@ -212,12 +212,16 @@ def test_camera_rays_match_reference_golden(r1, scenes, golden_rays, name):
     org, d = scenes[name].get_ray(g["seg_cam_su"][m], g["seg_cam_tv"][m], g["seg_cam_disk"][m])
     assert np.abs(org - g["seg_org"][m]).max() <= REL * np.abs(g["seg_org"][m]).max()
     assert np.abs(d - g["seg_dir"][m]).max() <= REL
-    # with the reference's own camera constants (folded at compile time there, <= 4 ulp from ours) getRay is bit-identical
-    s = r1.create_scene(name)
-    s.set_camera_raw(g["camera"], device=0)
-    org, d = s.get_ray(g["seg_cam_su"][m], g["seg_cam_tv"][m], g["seg_cam_disk"][m])
-    s.close()
+    # stronger: the binary's association, its normalise and its camera constants -> Camera::getRay is bit-identical
+    assert np.array_equal(bits(scenes[name].camera()), bits(g["camera"]))
     assert np.array_equal(bits(org), bits(g["seg_org"][m])) and np.array_equal(bits(d), bits(g["seg_dir"][m]))
+    # and r1_scene_set_camera_raw installs constants as given
+    s = r1.create_scene(name)
+    cam = g["camera"].copy(); cam[0] += 0.5
+    s.set_camera_raw(cam, device=0)
+    org2, _ = s.get_ray(g["seg_cam_su"][m][:8], g["seg_cam_tv"][m][:8], np.zeros((8, 2), np.float32))
+    s.close()
+    assert np.allclose(org2[:, 0], cam[0]) and not np.allclose(org2[:, 0], g["camera"][0])
 
 
 # ---- RNG ------------------------------------------------------------------------------------------------------------------------
@@ -557,25 +561,15 @@ def test_scene_above_staging_limit(r1, tmp_path):
 def test_per_pixel_replay_matches_reference_color(r1, scenes, golden_rays, name):
     """the GPU integrator (production scan / exact test / scatter / sky, the reference's generators replayed
     from recorded states) against the colour the reference's own color() returned for the same 4096 samples per scene.
-    Path-level parity: RNG consumption order, depth logic, attenuation order, ray counting.  With the reference's recorded
-    camera constants installed the result is BIT-IDENTICAL: every ray count and every float colour.  With the camera constants
-    evaluated at run time (<= 4 ulp away) primary rays differ in the last bit and a few percent of the samples take another
-    path (far hits are that sensitive), hence fractions for that case."""
+    Path-level parity: RNG consumption order, depth logic, attenuation order, ray counting.  The result is BIT-IDENTICAL: every
+    ray count and every float colour, on all four scenes."""
     from conftest import GOLDEN
     g = dict(np.load(os.path.join(GOLDEN, "replay_%s.npz" % name)))
     col, rays = scenes[name].replay_pixels(g["xy"], 1280, 720, 1, g["state"], g["state4"])
-    err = np.abs(col - g["color"]).max(axis=1)
-    same_rays, close = float((rays == g["rays"]).mean()), float((err < 1e-3).mean())
-    assert same_rays >= 0.95 and close >= 0.95 and np.median(err) < 1e-6, (same_rays, close, float(np.median(err)))
-    s = r1.create_scene(name)
-    s.set_camera_raw(golden_rays[name]["camera"], device=0)
-    col, rays = s.replay_pixels(g["xy"], 1280, 720, 1, g["state"], g["state4"])
     record("replay_4096_samples/%s" % name, {"same_ray_count": float((rays == g["rays"]).mean()),
-                                             "colour_bit_identical": float((bits(col) == bits(g["color"])).all(axis=1).mean()),
-                                             "with_runtime_camera_constants_same_ray_count": same_rays})
+                                             "colour_bit_identical": float((bits(col) == bits(g["color"])).all(axis=1).mean())})
     assert np.array_equal(rays, g["rays"])
     assert np.array_equal(bits(col), bits(g["color"]))
     # depth cap honoured: with max_bounces = 3 no sample traces more than 4 rays
-    col3, rays3 = s.replay_pixels(g["xy"][:512], 1280, 720, 1, g["state"][:512], g["state4"][:512], max_bounces=3)
-    s.close()
+    col3, rays3 = scenes[name].replay_pixels(g["xy"][:512], 1280, 720, 1, g["state"][:512], g["state4"][:512], max_bounces=3)
     assert rays3.max() <= 4

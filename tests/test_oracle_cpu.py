@@ -85,8 +85,16 @@ def test_scene_soa_matches_reference(oracle, golden_rays, name):
     assert np.array_equal(soa["kind"], g["soa_kind"])
     # albedo / ior / fuzz: x / 255.0f, 1.2f + i * 0.05f, 0.01f + 0.5f * y / H evaluated the way the fast-math build does
     assert np.array_equal(bits(soa["albedo"]), bits(g["soa_albedo"])) and np.array_equal(bits(soa["param"]), bits(g["soa_param"]))
-    # camera constants: gcc folds Camera::init at compile time; a run-time evaluation of rayweek1.cpp:366-379 is within 4 ulp
-    np.testing.assert_allclose(oracle.scene_camera(s), g["camera"], rtol=1e-6, atol=4e-6)
+    # camera constants: gcc folds Camera::init at compile time AFTER its fast-math reassociation (vfov * (pi * (1 / 360)));
+    # restated that way they are bit-identical; the source order (as_built = 0) is within 4 ulp
+    assert np.array_equal(bits(oracle.scene_camera(s)), bits(g["camera"]))
+    oracle.lib.orc_set_as_built(0)
+    try:
+        s0 = oracle.scene_create(name)
+        np.testing.assert_allclose(oracle.scene_camera(s0), g["camera"], rtol=1e-6, atol=4e-6)
+        oracle.scene_destroy(s0)
+    finally:
+        oracle.lib.orc_set_as_built(1)
     oracle.scene_destroy(s)
 
 
@@ -170,11 +178,7 @@ def test_camera_rays_match_reference(oracle, golden_rays, name):
     s = oracle.scene_create(name)
     m = g["seg_depth"] == 0
     org, d = oracle.get_ray(s, g["seg_cam_su"][m], g["seg_cam_tv"][m], g["seg_cam_disk"][m])
-    assert np.abs(org - g["seg_org"][m]).max() < 2e-6
-    assert np.abs(d - g["seg_dir"][m]).max() < 1e-6
-    # with the reference's own (compile-time folded) camera constants Camera::getRay is reproduced bit for bit
-    oracle.scene_set_camera(s, g["camera"])
-    org, d = oracle.get_ray(s, g["seg_cam_su"][m], g["seg_cam_tv"][m], g["seg_cam_disk"][m])
+    # Camera::getRay reproduced bit for bit (the binary's association, its rsqrtss + Newton normalise, its camera constants)
     assert np.array_equal(bits(org), bits(g["seg_org"][m])) and np.array_equal(bits(d), bits(g["seg_dir"][m]))
     oracle.scene_destroy(s)
 
@@ -247,18 +251,24 @@ def replay_agreement(col, rays, g):
 @pytest.mark.parametrize("name", ALL)
 def test_per_pixel_replay_matches_reference_color(oracle, golden_rays, name):
     """the pixel loop driven by the reference's generators from recorded states reproduces the colour the
-    reference's own color() returned -- BIT FOR BIT, ray counts included, for all 4096 recorded samples per scene, once the
-    reference's compile-time folded camera constants are installed.  (With camera constants evaluated at run time, <= 4 ulp
-    away, primary rays differ in the last bit and 1-4 % of the samples take another path: far hits are that sensitive.)"""
+    reference's own color() returned -- BIT FOR BIT, ray counts included, for all 4096 recorded samples per scene."""
     g = dict(np.load(os.path.join(GOLDEN, "replay_%s.npz" % name)))
     s = oracle.scene_create(name)
     col, rays = oracle.replay_pixels(s, g["xy"], 1280, 720, 1, g["state"], g["state4"])
-    same_rays, close, med = replay_agreement(col, rays, g)
-    assert same_rays >= 0.95 and close >= 0.95 and med < 1e-6, (same_rays, close, med)
-    oracle.scene_set_camera(s, golden_rays[name]["camera"])
-    col, rays = oracle.replay_pixels(s, g["xy"], 1280, 720, 1, g["state"], g["state4"])
     assert np.array_equal(rays, g["rays"])
     assert np.array_equal(bits(col), bits(g["color"]))
+    # how sensitive this is: camera constants <= 4 ulp away (the source-order evaluation) already send 0-4 % of the samples
+    # down another path -- far hits amplify the last bit of a primary ray
+    oracle.lib.orc_set_as_built(0)
+    try:
+        s0 = oracle.scene_create(name)
+    finally:
+        oracle.lib.orc_set_as_built(1)
+    oracle.scene_set_camera(s, oracle.scene_camera(s0))
+    col, rays = oracle.replay_pixels(s, g["xy"], 1280, 720, 1, g["state"], g["state4"])
+    same_rays, close, med = replay_agreement(col, rays, g)
+    assert 0.95 <= same_rays and close >= 0.95 and med < 1e-6, (same_rays, close, med)
+    oracle.scene_destroy(s0)
     oracle.scene_destroy(s)
 
 

@@ -8,12 +8,12 @@ namespace r1 {
 
 constexpr unsigned kFull = 0xffffffffu;
 
-// Work decomposition: unit u = (local pixel lp, sample chunk c), u = lp * n_chunks + c: `samples_per_unit` consecutive
-// samples of one pixel (1 sample for spp <= 256).  Lanes take RANGES of consecutive units from one global counter --
-// 16 units at a time while there is plenty of work, down to 1 near the end, so the last lanes finish within one sample of
-// each other -- and add every finished sample to the pixel's accumulator in 64-bit FIXED POINT (2^-24) with a
+// Work decomposition.  r1::megakernel_pool (default): work items are single samples g = lp * spp + s, handed to WARPS 32..2048
+// at a time from one 64-bit counter.  r1::megakernel (round-1 scheduling, R1_POOL=0) and the wavefront variant: unit
+// u = lp * n_chunks + c = `samples_per_unit` consecutive samples of one pixel (1 sample for spp <= 256), handed to LANES from a
+// 32-bit counter.  Either way every finished sample is added to its pixel's accumulator in 64-bit FIXED POINT (2^-24) with a
 // fire-and-forget atomic (RED.ADD.64).  Integer addition is associative: the sums, and therefore the RGB8 image, are
-// bit-identical for every GPU count, CTA shape, unit size and kernel variant, whatever order the samples arrive in.
+// bit-identical for every GPU count, CTA shape, scheduling and kernel variant, whatever order the samples arrive in.
 // (The reference sums floats sequentially per pixel, rayweek1.cpp:757-765; radiance per sample is in [0, 1], so 24
 // fractional bits lose < 3e-8 per sample -- float32 itself resolves no better near 1 -- and 2^20 samples fit with room.)
 struct RenderArgs {
@@ -29,14 +29,15 @@ struct RenderArgs {
     float inv_w, inv_h, inv_spp;
     uint64_t seed;                   // Rng::seed_hash(global seed)
     uint64_t magic_chunks, magic_width, magic_row_tile;  // floor(2^64 / d) + 1: exact n / d for 32-bit n via one 64-bit mul-high (0 when d == 1)
-    uint32_t sched_kmax, sched_div;      // unit ranges: a lane takes min(kmax, max(1, units_left / (lanes * div))) units per fetch
+    uint32_t sched_kmax, sched_div;      // guided self-scheduling: min(kmax, max(1, left / (lanes * div))) units per lane (megakernel) or
+                                         // x 32 samples per warp (megakernel_pool) per atomic
     // sample-pool scheduling (megakernel_pool): work items are single samples g = lp * spp + s, handed out 32 at a time
     unsigned long long *sample_counter;  // next sample to hand out (64-bit: 3840 x 2160 x 1024 = 8.5e9 samples)
     uint64_t n_samples, magic_spp;       // npix_local * spp; floor(2^64 / spp) + 1 (exact g / spp for g < 2^64 / spp; 0 when spp == 1)
 };
 
 constexpr int kSmemSpheres = 16 + R1_RSQRT12_ENTRIES * 2;   // megakernel: byte offset of the staged spheres (mbarrier, rsqrtss table first)
-constexpr float kFixedScale = 16777216.0f;                 // 2^24: one sample (clamped to 4.0) is < 2^26, so 32 samples sum in 32 bits
+constexpr float kFixedScale = 16777216.0f;                 // 2^24: one sample (clamped to 4.0) is < 2^26
 constexpr float kFixedInvScale = 5.9604644775390625e-8f;   // 2^-24
 
 // n / d for n, d < 2^32 with the precomputed magic (d == 1 -> magic 0)

@@ -35,6 +35,7 @@ thread_local std::string g_error;
 struct DeviceCtx {
     int device = -1;
     void *block = nullptr;
+    size_t block_bytes = 0;
     r1::DevScene dev;
 };
 
@@ -51,6 +52,11 @@ struct Scratch {
     unsigned long long *num_rays = nullptr;
     unsigned long long *host_rays = nullptr;  // pinned
     r1::WavefrontBuffers wf;
+    // scene blocks of destroyed scenes, kept for the next commit on this device: the reference-facing call builds a new scene
+    // per benchmark() (rayweek1.cpp:969-984), and a cudaMalloc + cudaFree per scene and device is most of what the 8-GPU
+    // in-process path pays on top of the render (8 serial commits inside a 13 ms step)
+    struct Block { void *ptr; size_t bytes; };
+    std::vector<Block> scene_blocks;
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
     uint32_t last_launches = 0, last_units = 0;
     uint64_t last_samples = 0;
@@ -85,12 +91,43 @@ struct r1_scene {
 
 namespace {
 
+constexpr size_t kSceneBlockCache = 4;   // blocks kept per device (<= 4 x 260 KB)
+
 void free_ctx(DeviceCtx &c)
 {
     if (c.device < 0) return;
-    cudaSetDevice(c.device);
-    cudaFree(c.block);
+    bool kept = false;
+    {
+        std::lock_guard<std::mutex> lock(g_scratch_mutex);
+        auto it = g_scratch.find(c.device);
+        if (it != g_scratch.end() && it->second.ready && it->second.scene_blocks.size() < kSceneBlockCache) {
+            it->second.scene_blocks.push_back({ c.block, c.block_bytes });
+            kept = true;
+        }
+    }
+    if (!kept) {
+        cudaSetDevice(c.device);
+        cudaFree(c.block);
+    }
     c = DeviceCtx();
+}
+
+// a device block of at least `bytes` for a scene: from the device's cache of released blocks, else cudaMalloc
+int take_scene_block(Scratch &scr, size_t bytes, void **out, size_t *out_bytes)
+{
+    {
+        std::lock_guard<std::mutex> lock(g_scratch_mutex);
+        for (size_t i = 0; i < scr.scene_blocks.size(); ++i) {
+            if (scr.scene_blocks[i].bytes >= bytes && scr.scene_blocks[i].bytes <= 2 * bytes + 4096) {
+                *out = scr.scene_blocks[i].ptr; *out_bytes = scr.scene_blocks[i].bytes;
+                scr.scene_blocks.erase(scr.scene_blocks.begin() + (long)i);
+                return R1_OK;
+            }
+        }
+    }
+    R1_CUDA(cudaMalloc(out, bytes));
+    *out_bytes = bytes;
+    return R1_OK;
 }
 
 int get_scratch(int device, Scratch **out)
@@ -419,7 +456,8 @@ int r1_scene_commit(r1_scene *scene, int device)
         }
         shade[2 * i + 1] = make_float4(inv_r, kind_bits, inv_ior, r0s);
     }
-    R1_CUDA(cudaMalloc(&c.block, bytes));
+    rc = take_scene_block(*scr, bytes, &c.block, &c.block_bytes);
+    if (rc) return rc;
     {
         const cudaError_t e = cudaMemcpy(c.block, host.data(), bytes, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { cudaFree(c.block); return fail(R1_ERR_CUDA, "scene upload: %s", cudaGetErrorString(e)); }

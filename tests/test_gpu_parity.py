@@ -409,6 +409,34 @@ def test_edge_sizes_and_depth_cap(r1, scenes):
     assert res.num_samples == 640 * 360
 
 
+def test_outputs_stay_inside_the_callers_buffers(r1, scenes):
+    """(compute-sanitizer is closed on this GPU pool.)  Host side: r1_render / benchmark() write exactly rows * width * 3 bytes --
+    guard bytes on both sides of the caller's buffer stay untouched, for ragged sizes and for a rank's share.  Device side: the
+    device-buffer entry point leaves a guard band behind d_rgb and around d_num_rays alone."""
+    import ctypes as C
+    import torch
+    s = scenes["medium"]
+    for (w, h, spp, rank, world) in ((33, 7, 3, 0, 1), (129, 65, 2, 1, 3), (640, 360, 1, 0, 1)):
+        rows = r1.local_rows(h, r1.DEFAULT_ROW_TILE, rank, world)
+        n = rows * w * 3
+        raw = np.full(n + 512, 0xA5, np.uint8)
+        p = r1.RenderParams(w, h, spp, 50, 0, 0, rank, world, r1.DEFAULT_ROW_TILE, 0, 0, -1)
+        res = r1.Result()
+        r1._check(r1.lib.r1_render(s.handle, C.byref(p), raw[256:256 + n], C.byref(res)), "r1_render")
+        assert (raw[:256] == 0xA5).all() and (raw[256 + n:] == 0xA5).all() and res.num_samples == rows * w * spp
+        ref, _ = s.render(w, h, spp, rank=rank, world=world)
+        assert np.array_equal(raw[256:256 + n].reshape(rows, w, 3), ref)
+    w, h, spp = 200, 117, 4
+    guard = 4096
+    d_rgb = torch.full((h * w * 3 + guard,), 0x5A, dtype=torch.uint8, device="cuda:0")
+    d_rays = torch.full((3,), -1, dtype=torch.int64, device="cuda:0")
+    s.render_device(d_rgb.data_ptr(), d_rays[1:].data_ptr(), torch.cuda.current_stream().cuda_stream, width=w, height=h, spp=spp, device=0)
+    torch.cuda.synchronize()
+    assert bool((d_rgb[h * w * 3:] == 0x5A).all()) and int(d_rays[0]) == -1 and int(d_rays[2]) == -1 and int(d_rays[1]) > w * h * spp
+    ref, rr = s.render(w, h, spp)
+    assert np.array_equal(d_rgb[: h * w * 3].cpu().numpy().reshape(h, w, 3), ref) and int(d_rays[1]) == rr.num_rays
+
+
 # ---- the reference's surface ------------------------------------------------------------------------------------------------
 
 def test_benchmark_surface(r1, tmp_path, monkeypatch, capfd):

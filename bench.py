@@ -241,6 +241,7 @@ def main():
     scene_name, W, H, SPP, MB = WORKLOADS[args.workload]
     config = {"workload": workload_label(args.workload), "scene": scene_name, "width": W, "height": H, "spp": SPP, "max_bounces": MB,
               "partition": "interleaved row tiles of 1 row, row k -> rank k %% %d" % world, "variant": args.variant,
+              "scheduling": "lane fetch (R1_POOL=0)" if os.environ.get("R1_POOL") == "0" else "warp sample pool",
               "l2": "flushed between timed steps (256 MiB write); the kernel's inputs (<= 128 KB of spheres) are staged to shared memory"}
 
     # -------------------------------------------------------------------------------------------- reference arm

@@ -261,8 +261,8 @@ int validate(const r1_render_params *p)
     if (p->width <= 0 || p->height <= 0 || p->spp <= 0 || p->max_bounces < 0) return fail(R1_ERR_ARG, "width/height/spp must be > 0, max_bounces >= 0");
     if (p->world <= 0 || p->rank < 0 || p->rank >= p->world) return fail(R1_ERR_ARG, "bad rank/world %d/%d", p->rank, p->world);
     if ((uint64_t)p->width * (uint64_t)p->height > (1ull << 31)) return fail(R1_ERR_ARG, "image too large");
-    // the pixel accumulators hold sums of radiance * 2^40 in 64 bits with samples clamped to 4.0 (r1_kernels.cuh): 2^22 samples
-    // would wrap; 2^20 is the documented limit
+    // the pixel accumulators hold sums of radiance * 2^24 in 64 bits, one sample saturating at 2^32 - 1 (r1_kernels.cuh): 2^20
+    // samples per pixel cannot wrap them
     if (p->spp > (1 << 20)) return fail(R1_ERR_LIMIT, "spp %d exceeds the accumulator limit of 2^20 samples per pixel", p->spp);
     if (p->variant < 0 || p->variant > 4) return fail(R1_ERR_ARG, "unknown variant %d", p->variant);
     return R1_OK;

@@ -355,3 +355,25 @@ def test_bench_steps_tool_compiles_the_executable(r1):
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.strip().splitlines()[-1] == "compiled " + r1.EXE_PATH
     assert os.access(r1.EXE_PATH, os.X_OK) and "RUN " not in out.stdout
+
+
+def test_header_is_plain_c_and_links(r1, tmp_path):
+    """include/rays1_b200.h is the boundary a C (cgo / FFI) binding would consume: it compiles as strict C99 and a C program
+    links against the library with nothing but that header"""
+    src = tmp_path / "abi.c"
+    src.write_text('#include "rays1_b200.h"\n'
+                   'int main(void) {\n'
+                   '    r1_render_params p; r1_result r; (void)p; (void)r;\n'
+                   '    if (r1_abi_version() != R1_ABI_VERSION) return 1;\n'
+                   '    r1_scene *s = r1_scene_create(8);\n'
+                   '    if (r1_scene_add_sphere(s, 0, 0, 0, 1.0f, R1_MAT_LAMBERT, .5f, .5f, .5f, 0) != 0) return 2;\n'
+                   '    if (r1_scene_pad(s, 8) != R1_OK || r1_scene_count(s) != 8) return 3;\n'
+                   '    if (r1_scene_commit(s, 0) != R1_ERR_STATE) return 4;   /* camera not set */\n'
+                   '    r1_scene_destroy(s);\n'
+                   '    return 0;\n}\n')
+    exe = tmp_path / "abi"
+    lib_dir = os.path.dirname(r1.LIB_PATH)
+    out = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                          "-L", lib_dir, "-lrays1_b200", "-Wl,-rpath," + lib_dir], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert subprocess.run([str(exe)]).returncode == 0

@@ -41,8 +41,9 @@ enum {
     R1_VARIANT_MEGAKERNEL_SCALAR = 2, /* A/B: megakernel with a per-lane scalar FFMA scan */
     R1_VARIANT_MEGAKERNEL_COOP = 3,   /* A/B: megakernel with the warp-cooperative scan (quads share sphere loads, candidates
                                          resolved through a per-warp shared-memory queue) */
-    R1_VARIANT_MEGAKERNEL_DEFERRED = 4 /* A/B: per-lane packed scan, candidates deferred to a per-warp queue and resolved once per
+    R1_VARIANT_MEGAKERNEL_DEFERRED = 4, /* A/B: per-lane packed scan, candidates deferred to a per-warp queue and resolved once per
                                          scan with every lane busy */
+    R1_VARIANT_MEGAKERNEL_DUAL = 5     /* A/B: two paths per lane share every sphere load (768 threads x 80 registers) */
 };
 
 typedef struct r1_scene r1_scene; /* opaque: host SoA + per-device buffers */

@@ -237,6 +237,30 @@ int launch_megakernel_pool(int sm_count, const r1::RenderArgs &args, const r1_re
     return R1_OK;
 }
 
+// two paths per lane (r1::megakernel_pool2, R1_VARIANT_MEGAKERNEL_DUAL)
+template <bool kStaged, int kThreads>
+int launch_megakernel_dual_t(int sm_count, const r1::RenderArgs &args, const r1_render_params &prm, cudaStream_t stream)
+{
+    auto kern = r1::megakernel_pool2<kStaged, kThreads, 1>;
+    const size_t smem = r1::kSmemSpheres + (kStaged ? (size_t)args.scene.n_pad * 32 : 0) + sizeof(r1::WarpPool) * (kThreads / 32);
+    R1_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = sm_count * (prm.blocks_per_sm > 0 ? prm.blocks_per_sm : 1);
+    const unsigned long long max_ctas = (args.n_samples + 2 * kThreads - 1) / (2 * kThreads);
+    if ((unsigned long long)grid > max_ctas) grid = (int)std::max<unsigned long long>(1, max_ctas);
+    kern<<<grid, kThreads, smem, stream>>>(args);
+    R1_CUDA(cudaGetLastError());
+    return R1_OK;
+}
+
+template <bool kStaged>
+int launch_megakernel_dual(int sm_count, const r1::RenderArgs &args, const r1_render_params &prm, cudaStream_t stream)
+{
+    const int threads = prm.threads > 0 ? prm.threads : 768;
+    if (threads == 512) return launch_megakernel_dual_t<kStaged, 512>(sm_count, args, prm, stream);
+    if (threads == 768) return launch_megakernel_dual_t<kStaged, 768>(sm_count, args, prm, stream);
+    return fail(R1_ERR_ARG, "the dual variant runs 512 or 768 threads (got %d)", threads);
+}
+
 template <int kScan, bool kStaged, int kThreads>
 int launch_megakernel_t(int sm_count, const r1::RenderArgs &args, const r1_render_params &prm, cudaStream_t stream)
 {
@@ -264,7 +288,7 @@ int validate(const r1_render_params *p)
     // the pixel accumulators hold sums of radiance * 2^24 in 64 bits, one sample saturating at 2^32 - 1 (r1_kernels.cuh): 2^20
     // samples per pixel cannot wrap them
     if (p->spp > (1 << 20)) return fail(R1_ERR_LIMIT, "spp %d exceeds the accumulator limit of 2^20 samples per pixel", p->spp);
-    if (p->variant < 0 || p->variant > 4) return fail(R1_ERR_ARG, "unknown variant %d", p->variant);
+    if (p->variant < 0 || p->variant > 5) return fail(R1_ERR_ARG, "unknown variant %d", p->variant);
     return R1_OK;
 }
 
@@ -591,6 +615,8 @@ int r1_render_device(r1_scene *scene, const r1_render_params *params, void *d_rg
                                                                             : launch_megakernel<r1::kScanCoop, false>(x.sm_count, a, prm, stream);
             else if (prm.variant == R1_VARIANT_MEGAKERNEL_DEFERRED) rc = staged ? launch_megakernel<r1::kScanLaneDeferred, true>(x.sm_count, a, prm, stream)
                                                                                 : launch_megakernel<r1::kScanLaneDeferred, false>(x.sm_count, a, prm, stream);
+            else if (prm.variant == R1_VARIANT_MEGAKERNEL_DUAL) rc = staged ? launch_megakernel_dual<true>(x.sm_count, a, prm, stream)
+                                                                            : launch_megakernel_dual<false>(x.sm_count, a, prm, stream);
             else rc = staged ? launch_megakernel<r1::kScanLaneScalar, true>(x.sm_count, a, prm, stream)
                              : launch_megakernel<r1::kScanLaneScalar, false>(x.sm_count, a, prm, stream);
             if (rc) return rc;

@@ -451,6 +451,149 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel_pool(const 
     if (lane == 0 && total) atomicAdd(a.num_rays, total);
 }
 
+// ------------------------------------------------------------------------------------------------ megakernel, two paths per lane
+// megakernel_pool with TWO paths per lane (R1_VARIANT_MEGAKERNEL_DUAL): both rays of a lane are tested against every sphere load,
+// so the chunk loop issues 32 LDS.128 per 64 ray-sphere tests instead of per 32 (181 instead of 202 instructions per 32 tests),
+// and a warp carries two independent FFMA2 streams.  The path state is 13 registers per path since the sample pool took the unit
+// bookkeeping out, so two paths fit a 768-thread CTA (80 registers) where round 1's two-path kernel needed 128 registers and 512
+// threads.  Everything else -- pool, production, shading, accumulators -- is megakernel_pool's; same bytes out.
+// Measured on B200: large 6095 (768 threads) / 6054 (512) against 6178 Mrays/s for one path per lane at 1024 threads, 4096-sphere
+// scene 820 against 825, medium 32.7 G against 34.1 G: the chunk loop is bound by the FMA pipe (FFMA2 / FADD2 issue), not by the
+// LDS count, so the saved loads buy nothing and the lower occupancy costs a little.  Kept as an A/B variant only.
+template <bool kStaged, int kThreads, int kBlocksPerSM>
+__global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel_pool2(const __grid_constant__ RenderArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint16_t *s_tab = reinterpret_cast<uint16_t *>(smem_raw + 16);
+    for (int i = threadIdx.x; i < R1_RSQRT12_ENTRIES / 2; i += kThreads)
+        reinterpret_cast<uint32_t *>(s_tab)[i] = reinterpret_cast<const uint32_t *>(g_rsqrt12)[i];
+    const float4 *s_scan, *s_exact;
+    if (kStaged) {
+        float4 *s_spheres = reinterpret_cast<float4 *>(smem_raw + kSmemSpheres);
+        stage_spheres(a.scene, s_spheres, reinterpret_cast<uint64_t *>(smem_raw));
+        s_scan = s_spheres;
+        s_exact = s_spheres + a.scene.n_pad;
+    } else {
+        s_scan = a.scene.scan;
+        s_exact = a.scene.exact;
+        __syncthreads();
+    }
+    const uint16_t *tab = s_tab;
+    const unsigned lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
+    WarpPool &pool = reinterpret_cast<WarpPool *>(smem_raw + kSmemSpheres + (kStaged ? (size_t)a.scene.n_pad * 32 : 0))[threadIdx.x >> 5];
+
+    bool active[2] = { false, false };
+    bool dry = false;                                            // warp-uniform
+    uint32_t ready = 0;                                          // warp-uniform
+    unsigned long long w_next = 0, w_end = 0;                    // warp-uniform private sample range
+    const uint32_t lanes_x = gridDim.x * blockDim.x * a.sched_div;
+    uint32_t lp[2] = { 0, 0 }, nrays = 0;
+    int depth[2] = { 0, 0 };
+    f3 thr[2] = { mk3(1, 1, 1), mk3(1, 1, 1) };
+    f3 o[2] = { mk3(0.0f, 1.0e18f, 0.0f), mk3(0.0f, 1.0e18f, 0.0f) }, d[2] = { mk3(0, 0, 0), mk3(0, 0, 0) };
+    Rng rng[2];
+    rng[0].k0 = rng[0].k1 = rng[1].k0 = rng[1].k1 = 0;
+
+    for (;;) {
+        // -- refill: slot 0 of every lane first, then slot 1 (ranks over the 64 slots of the warp)
+        const unsigned need0 = __ballot_sync(kFull, !active[0]), need1 = __ballot_sync(kFull, !active[1]);
+        if (need0 | need1) {
+            const uint32_t n0 = (uint32_t)__popc(need0), n_need = n0 + (uint32_t)__popc(need1);
+            const uint32_t rank[2] = { (uint32_t)__popc(need0 & lt_mask), n0 + (uint32_t)__popc(need1 & lt_mask) };
+            uint32_t served = 0;                                 // warp-uniform: slots with rank < served have been handled
+            for (;;) {
+                const uint32_t avail = ready;
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    if (!active[r] && rank[r] >= served && rank[r] < served + avail) {
+                        const int entry = (int)(avail - 1u - (rank[r] - served));
+                        const float4 ea = pool.a[entry], eb = pool.b[entry];
+                        if (__float_as_uint(ea.w) != kPoolInvalid) {
+                            o[r] = mk3(ea.x, ea.y, ea.z); d[r] = mk3(eb.x, eb.y, eb.z); lp[r] = __float_as_uint(ea.w);
+                            rng[r].k0 = __float_as_uint(eb.w); rng[r].k1 = pool.k1[entry];
+                            thr[r] = mk3(1, 1, 1); depth[r] = 0; active[r] = true;
+                        }
+                    }
+                }
+                const uint32_t take = min(avail, n_need - served);
+                ready -= take;
+                served += avail;
+                if (served >= n_need || dry) break;
+                // produce the next 32 samples (everything in the pool has been popped: ready == 0)
+                __syncwarp();
+                if (w_next >= w_end) {
+                    unsigned long long base = 0;
+                    uint32_t k = 1;
+                    if (lane == 0) {
+                        const unsigned long long left = a.n_samples > w_end ? a.n_samples - w_end : 0ull;
+                        const unsigned long long want_k = left / lanes_x;
+                        k = want_k >= a.sched_kmax ? a.sched_kmax : (want_k < 1 ? 1u : (uint32_t)want_k);
+                        base = atomicAdd(a.sample_counter, 32ull * k);
+                    }
+                    base = __shfl_sync(kFull, base, 0);
+                    k = __shfl_sync(kFull, k, 0);
+                    w_next = base;
+                    w_end = base + 32ull * k < a.n_samples ? base + 32ull * k : a.n_samples;
+                }
+                if (w_next >= a.n_samples) {
+                    dry = true;
+                } else {
+                    const unsigned long long g = w_next + lane;
+                    w_next += 32;
+                    float4 pa = make_float4(0, 0, 0, __uint_as_float(kPoolInvalid)), pb = make_float4(0, 0, 0, 0);
+                    uint32_t pk1 = 0;
+                    if (g < a.n_samples) {
+                        const uint32_t plp = a.magic_spp ? (uint32_t)__umul64hi(g, a.magic_spp) : (uint32_t)g;
+                        const uint32_t smp = (uint32_t)(g - (unsigned long long)plp * (uint32_t)a.spp);
+                        const uint32_t lr = fast_div(plp, a.magic_width);
+                        const int x = (int)(plp - lr * (uint32_t)a.width);
+                        const uint32_t tile = fast_div(lr, a.magic_row_tile);
+                        const int y = (int)((tile * (uint32_t)a.world + (uint32_t)a.rank) * (uint32_t)a.row_tile + (lr - tile * (uint32_t)a.row_tile));
+                        Rng r;
+                        f3 po, pd;
+                        primary_ray(a, (uint32_t)y * (uint32_t)a.width + (uint32_t)x, (float)x, (float)y, (int)smp, tab, r, po, pd);
+                        pa = make_float4(po.x, po.y, po.z, __uint_as_float(plp));
+                        pb = make_float4(pd.x, pd.y, pd.z, __uint_as_float(r.k0));
+                        pk1 = r.k1;
+                    }
+                    pool.a[lane] = pa; pool.b[lane] = pb; pool.k1[lane] = pk1;
+                    ready = 32;
+                }
+                __syncwarp();
+                if (dry) break;
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+                if (!active[r]) { o[r] = mk3(0.0f, 1.0e18f, 0.0f); d[r] = mk3(0.0f, 0.0f, 0.0f); }   // nothing left for this slot
+        }
+        // the warp is done when the work has run dry, the pool is empty and no slot holds a path
+        if (dry && ready == 0 && __all_sync(kFull, !active[0] && !active[1])) break;
+
+        // -- Hitable::hit for both rays against the same sphere loads
+        float t[2] = { kTMax, kTMax };
+        int hit[2] = { -1, -1 };
+        scan_dual(s_scan, s_exact, a.scene.n8, o, d, kTMin, t, hit);
+
+        // -- color() body for each live path
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (active[r]) {
+                ++nrays;
+                f3 contrib;
+                const float4 e = hit[r] >= 0 ? s_exact[hit[r]] : make_float4(0, 0, 0, 0);
+                if (shade_step(a, hit[r], t[r], e, tab, o[r], d[r], thr[r], depth[r], rng[r], contrib)) {
+                    accumulate_sample(a, lp[r], contrib);
+                    active[r] = false;
+                }
+            }
+        }
+    }
+    unsigned long long total = nrays;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(kFull, total, off);
+    if (lane == 0 && total) atomicAdd(a.num_rays, total);
+}
+
 // ------------------------------------------------------------------------------------------------ resolve
 // rayweek1.cpp:765-775: average, gamma 2 (sqrtf), quantise (int)(c * 255.99f) -> RGB8.
 __device__ __forceinline__ uint8_t quantise(unsigned long long sum, float inv_spp)

@@ -366,7 +366,7 @@ def test_bitwise_invariance(r1, scenes):
     base, r0 = s.render(w, h, spp)
     again, r1_ = s.render(w, h, spp)
     assert np.array_equal(base, again) and r0.num_rays == r1_.num_rays
-    for v in (r1.VARIANT_MEGAKERNEL_SCALAR, r1.VARIANT_MEGAKERNEL_COOP, r1.VARIANT_MEGAKERNEL_DEFERRED):
+    for v in (r1.VARIANT_MEGAKERNEL_SCALAR, r1.VARIANT_MEGAKERNEL_COOP, r1.VARIANT_MEGAKERNEL_DEFERRED, r1.VARIANT_MEGAKERNEL_DUAL):
         alt, ra = s.render(w, h, spp, variant=v)
         assert np.array_equal(base, alt) and ra.num_rays == r0.num_rays, v
     more, rm = s.render(w, h, spp, blocks_per_sm=2)
@@ -374,6 +374,11 @@ def test_bitwise_invariance(r1, scenes):
     for threads in (512, 768):
         alt, ra = s.render(w, h, spp, threads=threads)
         assert np.array_equal(base, alt) and ra.num_rays == r0.num_rays
+    alt, ra = s.render(w, h, spp, threads=512, variant=r1.VARIANT_MEGAKERNEL_DUAL)
+    assert np.array_equal(base, alt) and ra.num_rays == r0.num_rays
+    tiny, rt = s.render(7, 3, 5)                                  # fewer samples than one warp's 64 path slots
+    tiny2, rt2 = s.render(7, 3, 5, variant=r1.VARIANT_MEGAKERNEL_DUAL)
+    assert np.array_equal(tiny, tiny2) and rt.num_rays == rt2.num_rays
     wave, rw = s.render(w, h, spp, variant=r1.VARIANT_WAVEFRONT)
     assert np.array_equal(base, wave) and rw.num_rays == r0.num_rays
     assert rw.launches > 5
@@ -558,7 +563,7 @@ def test_unstaged_global_memory_scan_matches_staged(r1, scenes, monkeypatch):
     s = scenes["large"]
     base, r0 = s.render(160, 90, 24)
     monkeypatch.setenv("R1_FORCE_UNSTAGED", "1")
-    for v in (r1.VARIANT_MEGAKERNEL, r1.VARIANT_MEGAKERNEL_COOP, r1.VARIANT_MEGAKERNEL_SCALAR, r1.VARIANT_MEGAKERNEL_DEFERRED):
+    for v in (r1.VARIANT_MEGAKERNEL, r1.VARIANT_MEGAKERNEL_COOP, r1.VARIANT_MEGAKERNEL_SCALAR, r1.VARIANT_MEGAKERNEL_DEFERRED, r1.VARIANT_MEGAKERNEL_DUAL):
         alt, ra = s.render(160, 90, 24, variant=v)
         assert np.array_equal(base, alt) and ra.num_rays == r0.num_rays, v
 

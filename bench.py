@@ -227,7 +227,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="large", choices=sorted(WORKLOADS))
-    ap.add_argument("--variant", default="mega", choices=["mega", "wavefront", "scalar", "coop", "deferred", "dual"])
+    ap.add_argument("--variant", default="mega", choices=["mega", "wavefront", "scalar", "coop", "deferred", "dual", "tensor"])
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work per reference step / baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-exe", action="store_true", help="skip the `rays1_latest -n 3` run of the unmodified reference executable")

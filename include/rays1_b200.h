@@ -43,7 +43,9 @@ enum {
                                          resolved through a per-warp shared-memory queue) */
     R1_VARIANT_MEGAKERNEL_DEFERRED = 4, /* A/B: per-lane packed scan, candidates deferred to a per-warp queue and resolved once per
                                          scan with every lane busy */
-    R1_VARIANT_MEGAKERNEL_DUAL = 5     /* A/B: two paths per lane share every sphere load (768 threads x 80 registers) */
+    R1_VARIANT_MEGAKERNEL_DUAL = 5,    /* A/B: two paths per lane share every sphere load (768 threads x 80 registers) */
+    R1_VARIANT_MEGAKERNEL_TENSOR = 6   /* the filter as a TF32 GEMM on the tensor cores (tcgen05.mma, accumulators in TMEM), 128 rays x 64
+                                         spheres per instruction; scenes of up to 768 spheres */
 };
 
 typedef struct r1_scene r1_scene; /* opaque: host SoA + per-device buffers */
@@ -137,6 +139,10 @@ int r1_deinterleave_rows(int device, const void *d_gathered, uint64_t stride, vo
 /* Hitable::hit (rayweek1.cpp:152-339); index = -1 on a miss.  dir must be unit length (Ray ctor, :104-108). */
 int r1_trace_rays(r1_scene *scene, int n, const float *org, const float *dir, float t_min, float t_max, int variant,
                   int32_t *index, float *t, float *p, float *normal);
+/* Values of the tensor-core FILTER (R1_VARIANT_MEGAKERNEL_TENSOR) for n rays against every sphere: e[ray * n32 + sphere], n32 =
+ * sphere count padded to 32; the filter flags a sphere iff the sign bit of e is clear, and must flag every sphere Hitable::hit's
+ * discriminant test (rayweek1.cpp:192-204) accepts.  layout = 0. */
+int r1_filter_probe(r1_scene *scene, int n, const float *org, const float *dir, int layout, float *e);
 /* Material::scatter (rayweek1.cpp:403-409, 427-433, 470-511) with the random inputs injected: rand_sphere is the
  * unit-ball sample, rand_u the [0,1) uniform. */
 int r1_scatter(r1_scene *scene, int n, const float *dir_in, const float *p, const float *normal, const int32_t *index,

@@ -15,9 +15,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("R1_LIBRARY") or os.path.join(_HERE, "librays1_b200.so")   # R1_LIBRARY: an alternative build, for A/B runs
 EXE_PATH = os.path.join(_HERE, "rays1_b200")
 
-VARIANT_MEGAKERNEL, VARIANT_WAVEFRONT, VARIANT_MEGAKERNEL_SCALAR, VARIANT_MEGAKERNEL_COOP, VARIANT_MEGAKERNEL_DEFERRED, VARIANT_MEGAKERNEL_DUAL = 0, 1, 2, 3, 4, 5
+VARIANT_MEGAKERNEL, VARIANT_WAVEFRONT, VARIANT_MEGAKERNEL_SCALAR, VARIANT_MEGAKERNEL_COOP, VARIANT_MEGAKERNEL_DEFERRED, VARIANT_MEGAKERNEL_DUAL, VARIANT_MEGAKERNEL_TENSOR = 0, 1, 2, 3, 4, 5, 6
 VARIANTS = {"mega": VARIANT_MEGAKERNEL, "wavefront": VARIANT_WAVEFRONT, "scalar": VARIANT_MEGAKERNEL_SCALAR, "coop": VARIANT_MEGAKERNEL_COOP,
-            "deferred": VARIANT_MEGAKERNEL_DEFERRED, "dual": VARIANT_MEGAKERNEL_DUAL}
+            "deferred": VARIANT_MEGAKERNEL_DEFERRED, "dual": VARIANT_MEGAKERNEL_DUAL, "tensor": VARIANT_MEGAKERNEL_TENSOR}
 MAT_NONE, MAT_LAMBERT, MAT_METAL, MAT_DIELECTRIC = -1, 0, 1, 2
 
 # the reference's compile-time workload (src/common/common.h:18-25)
@@ -77,6 +77,7 @@ def _load():
         "r1_global_row": (ci, [ci, ci, ci, ci]),
         "r1_deinterleave_rows": (ci, [ci, vp, C.c_uint64, vp, ci, ci, ci, ci, vp]),
         "r1_trace_rays": (ci, [vp, ci, f32p, f32p, cf, cf, ci, i32p, f32p, f32p, f32p]),
+        "r1_filter_probe": (ci, [vp, ci, f32p, f32p, ci, f32p]),
         "r1_scatter": (ci, [vp, ci, f32p, f32p, f32p, i32p, f32p, f32p, i32p, f32p, f32p]),
         "r1_get_ray": (ci, [vp, ci, f32p, f32p, f32p, f32p, f32p]),
         "r1_replay_pixels": (ci, [vp, ci, i32p, ci, ci, ci, ci, u32p, u32p, f32p, u32p]),
@@ -201,6 +202,15 @@ class Scene:
         nrm = np.zeros((n, 3), np.float32)
         _check(lib.r1_trace_rays(self.handle, n, org, dir_, t_min, t_max, variant, idx, t, p, nrm), "r1_trace_rays")
         return idx, t, p, nrm
+
+    def filter_probe(self, org, dir_, n_spheres, layout=0):
+        """r1_filter_probe: values of the tensor-core filter, shape (rays, n32); sign bit clear = sphere flagged."""
+        org = np.ascontiguousarray(org, np.float32).reshape(-1, 3)
+        dir_ = np.ascontiguousarray(dir_, np.float32).reshape(-1, 3)
+        n, n32 = org.shape[0], (n_spheres + 31) // 32 * 32
+        e = np.zeros((n, n32), np.float32)
+        _check(lib.r1_filter_probe(self.handle, n, org, dir_, layout, e.reshape(-1)), "r1_filter_probe")
+        return e
 
     def scatter(self, dir_in, p, normal, index, rand_sphere, rand_u):
         c = lambda a, dt=np.float32: np.ascontiguousarray(a, dt)  # noqa: E731

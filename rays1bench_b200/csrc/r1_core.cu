@@ -261,6 +261,36 @@ int launch_megakernel_dual(int sm_count, const r1::RenderArgs &args, const r1_re
     return fail(R1_ERR_ARG, "the dual variant runs 512 or 768 threads (got %d)", threads);
 }
 
+// tensor-core filter (r1::megakernel_tc, R1_VARIANT_MEGAKERNEL_TENSOR): `threads` selects the number of 128-ray groups per CTA,
+// R1_TC_CFG="chunk,buffers" the TMEM pipeline (columns per accumulator buffer, buffers per group; groups x buffers x chunk <= 512)
+template <int kGroups, int kChunk, int kBufs>
+int launch_megakernel_tc_t(int sm_count, const r1::RenderArgs &args, cudaStream_t stream)
+{
+    auto kern = r1::megakernel_tc<kGroups, kChunk, kBufs>;
+    const size_t smem = r1::tc_smem_bytes(kGroups, args.scene.n32);
+    R1_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = sm_count;                                         // one CTA per SM: it owns all 512 TMEM columns
+    const unsigned long long max_ctas = (args.n_samples + kGroups * 128 - 1) / (kGroups * 128);
+    if ((unsigned long long)grid > max_ctas) grid = (int)std::max<unsigned long long>(1, max_ctas);
+    kern<<<grid, kGroups * 160, smem, stream>>>(args);
+    R1_CUDA(cudaGetLastError());
+    return R1_OK;
+}
+
+int launch_megakernel_tc(int sm_count, const r1::RenderArgs &args, const r1_render_params &prm, cudaStream_t stream)
+{
+    if (!args.scene.tcb) return fail(R1_ERR_LIMIT, "the tensor-core filter keeps at most %d spheres in shared memory", r1::tc::kMaxSpheres);
+    const int threads = prm.threads > 0 ? prm.threads : 512;
+    int chunk = 64, bufs = 2;
+    if (const char *e = getenv("R1_TC_CFG")) sscanf(e, "%d,%d", &chunk, &bufs);
+#define R1_TC_CASE(G, C, B) if (threads == G * 128 && chunk == C && bufs == B) return launch_megakernel_tc_t<G, C, B>(sm_count, args, stream)
+    R1_TC_CASE(4, 64, 2); R1_TC_CASE(4, 32, 4); R1_TC_CASE(4, 128, 1); R1_TC_CASE(4, 32, 2); R1_TC_CASE(4, 32, 3);
+    R1_TC_CASE(3, 64, 2); R1_TC_CASE(3, 32, 4);
+    R1_TC_CASE(2, 64, 2); R1_TC_CASE(2, 128, 2); R1_TC_CASE(2, 64, 4);
+#undef R1_TC_CASE
+    return fail(R1_ERR_ARG, "tensor variant: no kernel for %d ray threads, chunk %d, %d buffers", threads, chunk, bufs);
+}
+
 template <int kScan, bool kStaged, int kThreads>
 int launch_megakernel_t(int sm_count, const r1::RenderArgs &args, const r1_render_params &prm, cudaStream_t stream)
 {
@@ -288,7 +318,7 @@ int validate(const r1_render_params *p)
     // the pixel accumulators hold sums of radiance * 2^24 in 64 bits, one sample saturating at 2^32 - 1 (r1_kernels.cuh): 2^20
     // samples per pixel cannot wrap them
     if (p->spp > (1 << 20)) return fail(R1_ERR_LIMIT, "spp %d exceeds the accumulator limit of 2^20 samples per pixel", p->spp);
-    if (p->variant < 0 || p->variant > 5) return fail(R1_ERR_ARG, "unknown variant %d", p->variant);
+    if (p->variant < 0 || p->variant > 6) return fail(R1_ERR_ARG, "unknown variant %d", p->variant);
     return R1_OK;
 }
 
@@ -440,8 +470,11 @@ int r1_scene_commit(r1_scene *scene, int device)
     const int n = (int)scene->cx.size();
     const int n_pad = (n + 15) / 16 * 16;  // one scan supergroup = 16 spheres (the reference pads to SIMD_WIDTH = 8, rayweek1.cpp:575)
     const float inf = std::numeric_limits<float>::infinity();
-    // host image of the device block: [scan n_pad f4 | exact n_pad f4 | shade n_pad x 2 f4]
-    const size_t bytes = (size_t)n_pad * (16 + 16 + 32);
+    // host image of the device block: [scan n_pad f4 | exact n_pad f4 | shade n_pad x 2 f4 | tensor-filter operand n32 x 128 B]
+    const int n32 = (n + 31) / 32 * 32;
+    const bool tensor_ok = n32 <= r1::tc::kMaxSpheres;
+    const size_t tcb_off = (size_t)n_pad * (16 + 16 + 32);
+    const size_t bytes = tcb_off + (tensor_ok ? (size_t)n32 * r1::tc::kRowBytes : 0);
     std::vector<unsigned char> host(bytes, 0);
     float *scan = reinterpret_cast<float *>(host.data());
     float4 *exact = reinterpret_cast<float4 *>(host.data()) + n_pad;
@@ -480,6 +513,12 @@ int r1_scene_commit(r1_scene *scene, int device)
         }
         shade[2 * i + 1] = make_float4(inv_r, kind_bits, inv_ior, r0s);
     }
+    if (tensor_ok)
+        for (int i = 0; i < n32; ++i) {
+            const bool real = i < n && scene->inv_radius[i] != 0;
+            r1::tc::sphere_row_host(host.data() + tcb_off, i, real, real ? scene->cx[i] : 0.0, real ? scene->cy[i] : 0.0, real ? scene->cz[i] : 0.0,
+                                    real ? scene->radius_sq[i] : 0.0);
+        }
     rc = take_scene_block(*scr, bytes, &c.block, &c.block_bytes);
     if (rc) return rc;
     {
@@ -494,6 +533,8 @@ int r1_scene_commit(r1_scene *scene, int device)
     c.dev.n8 = (n + 7) / 8 * 8;
     c.dev.n_real = n;
     c.dev.cam = scene->cam;
+    c.dev.tcb = tensor_ok ? reinterpret_cast<const unsigned char *>(c.block) + tcb_off : nullptr;
+    c.dev.n32 = n32;
     scene->ctx[device] = c;
     scene->current = device;
     return R1_OK;
@@ -615,6 +656,7 @@ int r1_render_device(r1_scene *scene, const r1_render_params *params, void *d_rg
                                                                             : launch_megakernel<r1::kScanCoop, false>(x.sm_count, a, prm, stream);
             else if (prm.variant == R1_VARIANT_MEGAKERNEL_DEFERRED) rc = staged ? launch_megakernel<r1::kScanLaneDeferred, true>(x.sm_count, a, prm, stream)
                                                                                 : launch_megakernel<r1::kScanLaneDeferred, false>(x.sm_count, a, prm, stream);
+            else if (prm.variant == R1_VARIANT_MEGAKERNEL_TENSOR) rc = launch_megakernel_tc(x.sm_count, a, prm, stream);
             else if (prm.variant == R1_VARIANT_MEGAKERNEL_DUAL) rc = staged ? launch_megakernel_dual<true>(x.sm_count, a, prm, stream)
                                                                             : launch_megakernel_dual<false>(x.sm_count, a, prm, stream);
             else rc = staged ? launch_megakernel<r1::kScanLaneScalar, true>(x.sm_count, a, prm, stream)
@@ -753,6 +795,28 @@ int r1_trace_rays(r1_scene *scene, int n, const float *org, const float *dir, fl
     R1_CUDA(cudaDeviceSynchronize());
     R1_TRY(d_idx.download(index, (size_t)n * 4)); R1_TRY(d_t.download(t, (size_t)n * 4));
     R1_TRY(d_p.download(p, (size_t)n * 12)); R1_TRY(d_n.download(normal, (size_t)n * 12));
+    return R1_OK;
+}
+
+int r1_filter_probe(r1_scene *scene, int n, const float *org, const float *dir, int layout, float *e)
+{
+    DeviceCtx *cp = nullptr;
+    R1_TRY(get_ctx(scene, &cp));
+    if (n < 0 || (n > 0 && (!org || !dir || !e))) return fail(R1_ERR_ARG, "bad argument");
+    if (n == 0) return R1_OK;
+    if (!cp->dev.tcb) return fail(R1_ERR_LIMIT, "the tensor-core filter keeps at most %d spheres in shared memory", r1::tc::kMaxSpheres);
+    const int n32 = cp->dev.n32;
+    DevBuf d_org, d_dir, d_e;
+    R1_TRY(d_org.upload(org, (size_t)n * 12)); R1_TRY(d_dir.upload(dir, (size_t)n * 12));
+    R1_TRY(d_e.alloc((size_t)n * n32 * 4));
+    const size_t smem = 256 + (size_t)n32 * r1::tc::kRowBytes + 128 * r1::tc::kRowBytes;
+    R1_CUDA(cudaFuncSetAttribute(r1::tc_filter_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // layout 1 swaps the two stride fields of the shared-memory descriptors (bring-up aid; 0 is the layout the renderer uses)
+    const uint32_t lbo = layout == 1 ? r1::tc::kSBO : r1::tc::kLBO, sbo = layout == 1 ? r1::tc::kLBO : r1::tc::kSBO;
+    r1::tc_filter_probe_kernel<<<(n + 127) / 128, 160, smem>>>(cp->dev, n, d_org.as<float>(), d_dir.as<float>(), d_e.as<float>(), lbo, sbo);
+    R1_CUDA(cudaGetLastError());
+    R1_CUDA(cudaDeviceSynchronize());
+    R1_TRY(d_e.download(e, (size_t)n * n32 * 4));
     return R1_OK;
 }
 

@@ -3,6 +3,7 @@
 // file:line citations are relative to /root/reference/.
 #pragma once
 #include "r1_device.cuh"
+#include "r1_tensor.cuh"
 
 namespace r1 {
 
@@ -592,6 +593,337 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel_pool2(const
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(kFull, total, off);
     if (lane == 0 && total) atomicAdd(a.num_rays, total);
+}
+
+// ------------------------------------------------------------------------------------------------ megakernel, tensor-core filter
+// R1_VARIANT_MEGAKERNEL_TENSOR: the path state machine of megakernel_pool with the filter on the tensor cores (r1_tensor.cuh).
+//
+// CTA = kGroups ray groups of 128 threads (4 warps, warp w of a group owns TMEM lanes 32 w .. 32 w + 31, one ray per lane) +
+// one MMA-issuing warp per group.  Per scan every thread writes its ray's lifted TF32 row into the group's A tile; the issuing
+// warp then walks the scene's B tile (resident in shared memory) in chunks of 64 spheres: four tcgen05.mma (M = 128, N = 64,
+// K = 8) per chunk into one of the group's two 64-column accumulator buffers, tcgen05.commit onto the buffer's `full` mbarrier.
+// The ray warps wait for `full`, read their 64 filter values with two tcgen05.ld, release the buffer (`empty`, one arrival per
+// warp) and resolve the flagged spheres with the same exact test as every other variant -- same hits, same bytes out.
+// TMEM: kGroups x 2 buffers x 64 columns = all 512 columns at kGroups = 4.
+struct TcControl {
+    uint64_t a_full[4];               // per group: the four ray warps have written their rows (count 4)
+    uint64_t full[4][4];              // per group and buffer: accumulator chunk complete (tcgen05.commit, count 1)
+    uint64_t empty[4][4];             // per group and buffer: the four ray warps have read it (count 4)
+    uint32_t tmem_base;
+    uint32_t exit_flag[4];            // per group: set by the issuing warp once all four ray warps are out of work
+    uint32_t done[4][4];              // per group and ray warp: out of work (dry, pool empty, no live path)
+    uint32_t pad_[3];
+};
+static_assert(sizeof(TcControl) % 16 == 0, "TcControl is followed by 16-byte aligned tiles");
+
+// Lanes without a path take a ray from the warp's pool; the warp refills the pool when it runs short (megakernel_pool's refill).
+struct PoolState {
+    bool dry;
+    uint32_t ready;
+    unsigned long long w_next, w_end;
+};
+__device__ __forceinline__ void pool_take(const RenderArgs &a, WarpPool &pool, PoolState &ps, const uint16_t *tab, unsigned lane, unsigned lt_mask,
+                                          uint32_t lanes_x, unsigned need, bool want, bool &active, bool &exhausted, f3 &o, f3 &d, uint32_t &lp, Rng &rng,
+                                          f3 &thr, int &depth)
+{
+    const uint32_t n_need = (uint32_t)__popc(need), rank = (uint32_t)__popc(need & lt_mask);
+    int entry = -1;
+    if (want && rank < ps.ready) entry = (int)(ps.ready - 1u - rank);
+    const uint32_t n_first = min(n_need, ps.ready);
+    float4 ea = make_float4(0, 0, 0, __uint_as_float(kPoolInvalid)), eb = make_float4(0, 0, 0, 0);
+    uint32_t ek1 = 0;
+    if (entry >= 0) { ea = pool.a[entry]; eb = pool.b[entry]; ek1 = pool.k1[entry]; }
+    if (n_need > ps.ready && !ps.dry) {                          // warp-uniform: produce the next 32 samples
+        __syncwarp();
+        if (ps.w_next >= ps.w_end) {
+            unsigned long long base = 0;
+            uint32_t k = 1;
+            if (lane == 0) {
+                const unsigned long long left = a.n_samples > ps.w_end ? a.n_samples - ps.w_end : 0ull;
+                const unsigned long long want_k = left / lanes_x;
+                k = want_k >= a.sched_kmax ? a.sched_kmax : (want_k < 1 ? 1u : (uint32_t)want_k);
+                base = atomicAdd(a.sample_counter, 32ull * k);
+            }
+            base = __shfl_sync(kFull, base, 0);
+            k = __shfl_sync(kFull, k, 0);
+            ps.w_next = base;
+            ps.w_end = base + 32ull * k < a.n_samples ? base + 32ull * k : a.n_samples;
+        }
+        if (ps.w_next >= a.n_samples) {
+            ps.dry = true;
+            ps.ready = 0;
+        } else {
+            const unsigned long long g = ps.w_next + lane;
+            ps.w_next += 32;
+            float4 pa = make_float4(0, 0, 0, __uint_as_float(kPoolInvalid)), pb = make_float4(0, 0, 0, 0);
+            uint32_t pk1 = 0;
+            if (g < a.n_samples) {
+                const uint32_t plp = a.magic_spp ? (uint32_t)__umul64hi(g, a.magic_spp) : (uint32_t)g;
+                const uint32_t smp = (uint32_t)(g - (unsigned long long)plp * (uint32_t)a.spp);
+                const uint32_t lr = fast_div(plp, a.magic_width);
+                const int x = (int)(plp - lr * (uint32_t)a.width);
+                const uint32_t tile = fast_div(lr, a.magic_row_tile);
+                const int y = (int)((tile * (uint32_t)a.world + (uint32_t)a.rank) * (uint32_t)a.row_tile + (lr - tile * (uint32_t)a.row_tile));
+                Rng r;
+                f3 po, pd;
+                primary_ray(a, (uint32_t)y * (uint32_t)a.width + (uint32_t)x, (float)x, (float)y, (int)smp, tab, r, po, pd);
+                pa = make_float4(po.x, po.y, po.z, __uint_as_float(plp));
+                pb = make_float4(pd.x, pd.y, pd.z, __uint_as_float(r.k0));
+                pk1 = r.k1;
+            }
+            pool.a[lane] = pa; pool.b[lane] = pb; pool.k1[lane] = pk1;
+            ps.ready = 32;
+        }
+        __syncwarp();
+        const uint32_t rank2 = rank - n_first;                   // rank among the lanes the old pool could not serve
+        if (want && entry < 0 && rank2 < ps.ready) {
+            entry = (int)(ps.ready - 1u - rank2);
+            ea = pool.a[entry]; eb = pool.b[entry]; ek1 = pool.k1[entry];
+        }
+        ps.ready -= min(n_need - n_first, ps.ready);
+    } else {
+        ps.ready -= n_first;
+    }
+    if (want) {
+        if (entry >= 0 && __float_as_uint(ea.w) != kPoolInvalid) {
+            o = mk3(ea.x, ea.y, ea.z); d = mk3(eb.x, eb.y, eb.z); lp = __float_as_uint(ea.w);
+            rng.k0 = __float_as_uint(eb.w); rng.k1 = ek1;
+            thr = mk3(1, 1, 1); depth = 0; active = true;
+        } else {
+            exhausted = true;                                    // past the end of the work
+        }
+    }
+}
+
+constexpr size_t tc_smem_bytes(int groups, int n32)
+{
+    return (size_t)kSmemSpheres + sizeof(TcControl) + (size_t)n32 * tc::kRowBytes + (size_t)n32 * 16 + (size_t)groups * 128 * tc::kRowBytes +
+           (size_t)groups * 4 * sizeof(WarpPool) + 128;          // + alignment slack
+}
+
+template <int kGroups, int kChunk, int kBufs>
+__global__ void __launch_bounds__(kGroups * 160, 1) megakernel_tc(const __grid_constant__ RenderArgs a)
+{
+    static_assert(kGroups >= 1 && kGroups <= 4 && kBufs >= 1 && kBufs <= 4 && kChunk % 32 == 0 && kChunk <= 256, "bad configuration");
+    static_assert(kGroups * kBufs * kChunk <= 512, "TMEM has 512 columns");
+    constexpr int kPieces = kChunk / 32;
+    constexpr int kRayThreads = kGroups * 128;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // shared memory: [16 B | rsqrtss table 4 KB | control | B tile n32 x 128 B | exact n32 x 16 B | A tiles kGroups x 16 KB | pools]
+    uint16_t *s_tab = reinterpret_cast<uint16_t *>(smem_raw + 16);
+    unsigned char *p = smem_raw + ((kSmemSpheres + 127) & ~127);
+    TcControl &ctl = *reinterpret_cast<TcControl *>(p);
+    p += (sizeof(TcControl) + 127) & ~127;
+    unsigned char *s_b = p;
+    const int n32 = a.scene.n32;
+    p += (size_t)n32 * tc::kRowBytes;
+    float4 *s_exact = reinterpret_cast<float4 *>(p);
+    p += (size_t)n32 * 16;
+    unsigned char *s_a = p;
+    p += (size_t)kGroups * 128 * tc::kRowBytes;
+    WarpPool *pools = reinterpret_cast<WarpPool *>(p);
+
+    for (int i = threadIdx.x; i < R1_RSQRT12_ENTRIES / 2; i += blockDim.x)
+        reinterpret_cast<uint32_t *>(s_tab)[i] = reinterpret_cast<const uint32_t *>(g_rsqrt12)[i];
+    for (int i = threadIdx.x; i < n32 * (tc::kRowBytes / 16); i += blockDim.x)
+        reinterpret_cast<uint4 *>(s_b)[i] = reinterpret_cast<const uint4 *>(a.scene.tcb)[i];
+    for (int i = threadIdx.x; i < n32; i += blockDim.x)
+        s_exact[i] = i < a.scene.n_pad ? a.scene.exact[i] : make_float4(0, 0, 0, 0);
+    if (threadIdx.x == 0) {
+        for (int g = 0; g < 4; ++g) {
+            tc::mbar_init(&ctl.a_full[g], 4);
+            for (int b = 0; b < 4; ++b) { tc::mbar_init(&ctl.full[g][b], 1); tc::mbar_init(&ctl.empty[g][b], 4); }
+            ctl.exit_flag[g] = 0;
+        }
+        tc::fence_mbar_init();
+    }
+    tc::fence_proxy_async();                                     // the B tile is read by the tensor core (async proxy)
+    if (threadIdx.x < 32) tc::tmem_alloc(&ctl.tmem_base, 512);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(&ctl.tmem_base);
+    const int nchunks = (n32 + kChunk - 1) / kChunk;
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t nrays = 0;
+
+    if (threadIdx.x >= kRayThreads) {
+        // ===== MMA issuer of group g (one lane) =====
+        const int g = (threadIdx.x - kRayThreads) >> 5;
+        if (lane == 0) {
+            const uint32_t a_smem = tc::smem_u32(s_a + (size_t)g * 128 * tc::kRowBytes), b_smem = tc::smem_u32(s_b);
+            uint32_t it = 0;
+            for (uint32_t scan_no = 0;; ++scan_no) {
+                tc::mbar_wait(&ctl.a_full[g], scan_no & 1u);
+                const volatile uint32_t *dn = ctl.done[g];
+                if (dn[0] && dn[1] && dn[2] && dn[3]) {          // nobody has a path left: wake the group up and leave
+                    *reinterpret_cast<volatile uint32_t *>(&ctl.exit_flag[g]) = 1u;
+                    tc::mbar_arrive(&ctl.full[g][it % kBufs]);
+                    break;
+                }
+                tc::tc_fence_after();
+                for (int c = 0; c < nchunks; ++c, ++it) {
+                    const uint32_t b = it % kBufs;
+                    tc::mbar_wait(&ctl.empty[g][b], ((it / kBufs) & 1u) ^ 1u);
+                    tc::tc_fence_after();
+                    const int n = min(kChunk, n32 - c * kChunk);
+                    tc::mma_chunk(tmem_base + (uint32_t)(g * kBufs + (int)b) * kChunk, a_smem, b_smem + (uint32_t)c * (kChunk / 8) * tc::kSBO, n, tc::kLBO, tc::kSBO);
+                    tc::mma_commit(&ctl.full[g][b]);
+                }
+            }
+        }
+    } else {
+        // ===== ray warps =====
+        const int g = threadIdx.x >> 7, w = (threadIdx.x >> 5) & 3, r = threadIdx.x & 127;
+        const uint16_t *tab = s_tab;
+        const unsigned lt_mask = (1u << lane) - 1u;
+        WarpPool &pool = pools[threadIdx.x >> 5];
+        unsigned char *a_tile = s_a + (size_t)g * 128 * tc::kRowBytes;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(g * kBufs) * kChunk;
+        bool active = false, exhausted = false;
+        PoolState ps;
+        ps.dry = false; ps.ready = 0; ps.w_next = 0; ps.w_end = 0;
+        const uint32_t lanes_x = gridDim.x * kRayThreads * a.sched_div;
+        uint32_t lp = 0, it = 0;
+        int depth = 0;
+        f3 thr = mk3(1, 1, 1), o = mk3(0, 0, 0), d = mk3(0, 0, 0);
+        Rng rng;
+        rng.k0 = 0; rng.k1 = 0;
+
+        for (;;) {
+            const bool want = !active && !exhausted;
+            const unsigned need = __ballot_sync(kFull, want);
+            if (need) pool_take(a, pool, ps, tab, lane, lt_mask, lanes_x, need, want, active, exhausted, o, d, lp, rng, thr, depth);
+            const bool warp_done = __all_sync(kFull, exhausted);
+
+            tc::write_ray_row(a_tile, r, o, d, active);
+            tc::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                *reinterpret_cast<volatile uint32_t *>(&ctl.done[g][w]) = warp_done ? 1u : 0u;
+                tc::mbar_arrive(&ctl.a_full[g]);
+            }
+
+            float t = kTMax;
+            int hit = -1;
+            bool leave = false;
+            for (int c = 0; c < nchunks; ++c, ++it) {
+                const uint32_t b = it % kBufs;
+                tc::mbar_wait(&ctl.full[g][b], (it / kBufs) & 1u);
+                if (c == 0 && *reinterpret_cast<volatile uint32_t *>(&ctl.exit_flag[g])) { leave = true; break; }
+                tc::tc_fence_after();
+                const int pieces = min(kPieces, (n32 - c * kChunk) >> 5);   // warp-uniform: the last chunk may be short
+                uint32_t cand[kPieces];
+#pragma unroll
+                for (int h = 0; h < kPieces; ++h) {
+                    cand[h] = 0;
+                    if (h < pieces) {
+                        uint32_t v[32];
+                        tc::tmem_ld32(t_lane + b * kChunk + 32 * h, v);
+                        cand[h] = tc::flagged(v);
+                    }
+                }
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&ctl.empty[g][b]);
+#pragma unroll
+                for (int h = 0; h < kPieces; ++h)
+                    if (cand[h]) exact_candidates(cand[h], s_exact, c * kChunk + 32 * h, o, d, kTMin, t, hit);
+            }
+            if (leave) break;
+
+            if (active) {
+                ++nrays;
+                f3 contrib;
+                const float4 e = hit >= 0 ? s_exact[hit] : make_float4(0, 0, 0, 0);
+                if (shade_step(a, hit, t, e, tab, o, d, thr, depth, rng, contrib)) {
+                    accumulate_sample(a, lp, contrib);
+                    active = false;
+                }
+            }
+        }
+        unsigned long long total = nrays;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(kFull, total, off);
+        if (lane == 0 && total) atomicAdd(a.num_rays, total);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tc::tmem_dealloc(tmem_base, 512);
+}
+
+// Filter values of n rays against every sphere (parity / error measurement of the tensor filter): e[ray * n32 + sphere].
+// One CTA per 128 rays: 4 ray warps + the issuing warp, the scan of megakernel_tc with kGroups = 1 and the values written out.
+constexpr int kProbeChunk = 64;
+__global__ void __launch_bounds__(160, 1) tc_filter_probe_kernel(DevScene sc, int n, const float *__restrict__ org, const float *__restrict__ dir, float *__restrict__ e_out,
+                                                               uint32_t lbo, uint32_t sbo)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TcControl &ctl = *reinterpret_cast<TcControl *>(smem_raw);
+    unsigned char *s_b = smem_raw + ((sizeof(TcControl) + 127) & ~127);
+    const int n32 = sc.n32;
+    unsigned char *a_tile = s_b + (size_t)n32 * tc::kRowBytes;
+    for (int i = threadIdx.x; i < n32 * (tc::kRowBytes / 16); i += blockDim.x)
+        reinterpret_cast<uint4 *>(s_b)[i] = reinterpret_cast<const uint4 *>(sc.tcb)[i];
+    if (threadIdx.x == 0) {
+        tc::mbar_init(&ctl.a_full[0], 4);
+        for (int b = 0; b < 2; ++b) { tc::mbar_init(&ctl.full[0][b], 1); tc::mbar_init(&ctl.empty[0][b], 4); }
+        tc::fence_mbar_init();
+    }
+    tc::fence_proxy_async();
+    if (threadIdx.x < 32) tc::tmem_alloc(&ctl.tmem_base, 128);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(&ctl.tmem_base);
+    const int nchunks = (n32 + kProbeChunk - 1) / kProbeChunk;
+    const unsigned lane = threadIdx.x & 31u;
+    if (threadIdx.x >= 128) {
+        if (lane == 0) {
+            tc::mbar_wait(&ctl.a_full[0], 0);
+            tc::tc_fence_after();
+            uint32_t it = 0;
+            for (int c = 0; c < nchunks; ++c, ++it) {
+                const uint32_t b = it & 1u;
+                tc::mbar_wait(&ctl.empty[0][b], ((it >> 1) & 1u) ^ 1u);
+                tc::tc_fence_after();
+                const int nn = min(kProbeChunk, n32 - c * kProbeChunk);
+                tc::mma_chunk(tmem_base + b * kProbeChunk, tc::smem_u32(a_tile), tc::smem_u32(s_b) + (uint32_t)c * (kProbeChunk / 8) * tc::kSBO, nn, lbo, sbo);
+                tc::mma_commit(&ctl.full[0][b]);
+            }
+        }
+    } else {
+        const int r = threadIdx.x, w = threadIdx.x >> 5;
+        const int ray = blockIdx.x * 128 + r;
+        const bool live = ray < n;
+        f3 o = mk3(0, 0, 0), d = mk3(0, 0, 0);
+        if (live) { o = mk3(org[3 * ray], org[3 * ray + 1], org[3 * ray + 2]); d = mk3(dir[3 * ray], dir[3 * ray + 1], dir[3 * ray + 2]); }
+        tc::write_ray_row(a_tile, r, o, d, live);
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&ctl.a_full[0]);
+        const uint32_t t_lane = tmem_base + ((uint32_t)(w * 32) << 16);
+        uint32_t it = 0;
+        for (int c = 0; c < nchunks; ++c, ++it) {
+            const uint32_t b = it & 1u;
+            tc::mbar_wait(&ctl.full[0][b], (it >> 1) & 1u);
+            tc::tc_fence_after();
+            const int halves = n32 - c * kProbeChunk > 32 ? 2 : 1;
+            for (int h = 0; h < halves; ++h) {
+                uint32_t v[32];
+                tc::tmem_ld32(t_lane + b * kProbeChunk + 32 * h, v);
+                if (live)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) e_out[(size_t)ray * n32 + c * kProbeChunk + 32 * h + j] = __uint_as_float(v[j]);
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&ctl.empty[0][b]);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tc::tmem_dealloc(tmem_base, 128);
 }
 
 // ------------------------------------------------------------------------------------------------ resolve

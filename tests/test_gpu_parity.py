@@ -124,6 +124,73 @@ def test_filter_is_conservative_for_far_and_grazing_rays(r1, scenes, oracle, nam
     assert np.array_equal(bits(got[3][m]), bits(want[3][m]))
 
 
+def tensor_filter_rays(soa, n=4096, seed=99):
+    """fresh rays around the scene + rays grazing spheres from 5 .. 300 units away"""
+    rng = np.random.default_rng(seed)
+    org = (rng.normal(size=(n, 3)) * [8, 2, 8] + [0, 2, 0])
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    real = np.where(soa["inv_radius"] > 0)[0]
+    idx = rng.choice(real, n)
+    ctr = np.stack([soa["cx"][idx], soa["cy"][idx], soa["cz"][idx]], 1).astype(np.float64)
+    rad = 1.0 / soa["inv_radius"][idx].astype(np.float64)
+    u = rng.normal(size=(n, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    o2 = ctr + u * rng.choice([5.0, 50.0, 300.0], n)[:, None]
+    side = np.cross(u, rng.normal(size=(n, 3))); side /= np.linalg.norm(side, axis=1, keepdims=True)
+    d2 = ctr + side * (rad * rng.uniform(0.98, 1.02, n))[:, None] - o2
+    d2 /= np.linalg.norm(d2, axis=1, keepdims=True)
+    return np.concatenate([org, o2]).astype(np.float32), np.concatenate([d, d2]).astype(np.float32)
+
+
+def tensor_filter_truth(soa, org, d, margin=2.0 ** -16):
+    """float64 values of the filter polynomial and of Hitable::hit's discriminant for every (ray, sphere), from the float32 inputs"""
+    o, dd = org.astype(np.float64), d.astype(np.float64)
+    c = np.stack([soa["cx"], soa["cy"], soa["cz"]], 1).astype(np.float64)
+    r2 = soa["radius_sq"].astype(np.float64)
+    co = c[None, :, :] - o[:, None, :]
+    nb = (co * dd[:, None, :]).sum(2)
+    discr = nb * nb - ((co * co).sum(2) - r2[None, :])
+    big_s = (c * c).sum(1)[None, :] + (o * o).sum(1)[:, None]
+    return discr + margin * big_s, discr, big_s
+
+
+@pytest.mark.parametrize("name", ("large", "medium", "small"))
+def test_tensor_filter_is_conservative(r1, scenes, name):
+    """R1_VARIANT_MEGAKERNEL_TENSOR evaluates the filter as a TF32 GEMM with split operands (r1_tensor.cuh).  Its values must stay
+    within a fraction of the margin of the float64 polynomial, and every sphere whose discriminant the exact test could accept
+    (true value above minus the exact path's own rounding bound) must be flagged."""
+    soa = scenes[name].soa()
+    n_sph = len(soa["cx"])
+    org, d = tensor_filter_rays(soa)
+    e = scenes[name].filter_probe(org, d, n_sph).astype(np.float64)
+    want, discr, big_s = tensor_filter_truth(soa, org, d)
+    real = soa["inv_radius"] > 0
+    err = np.abs(e[:, :n_sph] - want)[:, real] / big_s[:, real]
+    record("tensor_filter_rel_err_%s" % name, {"max": float(err.max()), "p99.9": float(np.quantile(err, 0.999)), "margin": 2.0 ** -16})
+    assert err.max() < 0.1 * 2.0 ** -16, "tensor filter error %.3g of S eats the margin" % err.max()
+    must = (discr >= -4.0e-6 * big_s) & real[None, :]            # the exact path's rounding bound is 3.1e-6 S (DESIGN.md section 4.1)
+    assert must.sum() > 4000
+    assert (e[:, :n_sph][must] >= 0).all() and not np.signbit(e[:, :n_sph][must]).any()
+    assert (e[:, n_sph:] < 0).all() and (e[:, :n_sph][:, ~real] < 0).all(), "padding rows must never be flagged"
+    flagged = (~np.signbit(e[:, :n_sph])) & real[None, :]
+    record("tensor_filter_flag_ratio_%s" % name, float(flagged.sum() / max(1, ((discr >= 0) & real[None, :]).sum())))
+
+
+def test_tensor_variant_renders_the_same_bytes(r1, scenes):
+    """same hits, same bytes: the tensor-core filter only decides which spheres get the exact test"""
+    for name, (w, h, spp) in (("large", (200, 117, 40)), ("medium", (160, 90, 16)), ("small", (64, 36, 8)), ("large", (7, 3, 5))):
+        base, r0 = scenes[name].render(w, h, spp)
+        for threads in (512, 384, 256):
+            alt, ra = scenes[name].render(w, h, spp, variant=r1.VARIANT_MEGAKERNEL_TENSOR, threads=threads)
+            assert np.array_equal(base, alt) and ra.num_rays == r0.num_rays, (name, threads)
+    for world in (2, 3):
+        parts = [scenes["large"].render(200, 117, 40, rank=r, world=world, variant=r1.VARIANT_MEGAKERNEL_TENSOR)[0] for r in range(world)]
+        whole, _ = scenes["large"].render(200, 117, 40)
+        rows = [r1.global_row(lr, r1.DEFAULT_ROW_TILE, r, world) for r in range(world) for lr in range(parts[r].shape[0])]
+        assert np.array_equal(np.concatenate(parts)[np.argsort(rows)], whole)
+    with pytest.raises(r1.Rays1Error):
+        scenes["synth4096"].render(64, 36, 2, variant=r1.VARIANT_MEGAKERNEL_TENSOR)   # above the shared-memory limit of the B tile
+
+
 def test_hit_empty_and_single(r1, scenes):
     idx, t, p, n = scenes["small"].trace_rays(np.zeros((0, 3)), np.zeros((0, 3)))
     assert idx.shape == (0,)

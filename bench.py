@@ -227,7 +227,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="large", choices=sorted(WORKLOADS))
-    ap.add_argument("--variant", default="mega", choices=["mega", "wavefront", "scalar", "coop", "deferred", "dual", "tensor"])
+    ap.add_argument("--variant", default="mega", choices=["mega", "wavefront", "scalar", "coop", "deferred", "dual", "tensor", "packed"])
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work per reference step / baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-exe", action="store_true", help="skip the `rays1_latest -n 3` run of the unmodified reference executable")
@@ -306,6 +306,11 @@ def main():
     r1._check(r1.lib.r1_scene_commit(scene.handle, local_rank), "r1_scene_commit")
     n_real = r1.REAL_SPHERES[scene_name]
     n_pad = (scene.count() + 15) // 16 * 16
+    n32 = (scene.count() + 31) // 32 * 32
+    kernel = "r1::" + r1.lib.r1_kernel_name(scene.handle, variant).decode()   # what the variant resolves to for this scene
+    if args.threads and args.variant == "mega":
+        kernel = "r1::megakernel_pool"                                          # explicit tuning knobs address the packed kernel
+    traffic_key = "tensor" if "megakernel_tc" in kernel else ("mega" if args.variant == "packed" else args.variant)
 
     my_rows = r1.local_rows(H, row_tile, rank, world)
     max_rows = r1d.max_local_rows(H, row_tile, world)
@@ -431,24 +436,44 @@ def main():
     peak_nominal = sm_count * 128 * 2 * NOMINAL_SM_MHZ * 1e6 / 1e12
     achieved = total_rays * f_ray / (ms_trace * 1e-3) / 1e12 / world  # per GPU
     hbm_bytes = W * H * (32 * 2 + 3) + n_pad * 32 * sm_count   # fixed-point accumulators zeroed + written back, RGB8 out, staging
-    roofline = {"bound": "fp32_fma", "kernel": "r1::megakernel" if args.variant != "wavefront" else "r1::wf_intersect + wf_shade (graph loop)", "achieved": achieved,
+    roofline = {"bound": "fp32_fma", "kernel": kernel, "achieved": achieved,
                 "peak": peak_meas, "unit": "TFLOP/s", "frac": achieved / peak_meas,
                 "peak_source": "FFMA/FFMA2 chain microbenchmark on this GPU (r1_fma_peak), per GPU; scalar %.1f / packed %.1f TFLOP/s (SM clock during the run: see clocks)" %
                                (peak_scalar, peak_packed),
                 "peak_nominal": peak_nominal, "frac_nominal": achieved / peak_nominal,
                 "flops_per_ray": f_ray, "flops_model": "16 per ray-sphere test (FMA=2) x %d real spheres + 70 shading (SURVEY.md 8d)" % n_real,
-                "traffic": ncu_traffic(args.workload, args.variant)[0] if world == 1 else None,
-                "traffic_source": ncu_traffic(args.workload, args.variant)[1] if world == 1 else None,
+                "traffic": ncu_traffic(args.workload, traffic_key)[0] if world == 1 else None,
+                "traffic_source": ncu_traffic(args.workload, traffic_key)[1] if world == 1 else None,
                 "traffic_note": "DRAM bytes per launch of the dominant kernel (ncu --set full, profiles/ncu_traffic.json); algorithmic FLOPs are "
                                 "the REFERENCE's 16 per test, the filter executes 8 FMA-pipe instructions per test plus an exact re-test of "
                                 "the 0.4 % candidates",
                 "hbm": {"algorithmic_bytes_per_step": hbm_bytes, "achieved_gbs": hbm_bytes * args.steps / (ms_trace * 1e-3) / 1e9,
                         "note": "pixel accumulators (32 B, L2 atomics) + RGB8 out + sphere staging per CTA: HBM is idle on this path"}}
+    peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         roofline["hbm"]["peak_gbs"] = peaks.get("hbm_gbs")
     except (OSError, ValueError):
         pass
+    if "megakernel_tc" in kernel:
+        # The filter of this kernel runs on the tensor cores: 128 rays x n32 spheres x K = 32 split-TF32 MACs per scan, one 4-byte
+        # filter value per test read back from TMEM.  The FP32 roofline above keeps the ALGORITHMIC flops (the reference's 16 per
+        # test) against the FP32 FMA peak -- a fraction above 1 says the work left the FP32 pipe; the two hardware bounds of the
+        # filter as built are below.
+        tests = total_rays * n32 / world                                      # per GPU, padded columns included
+        tf32_exec = tests * 2 * 32 / (ms_trace * 1e-3) / 1e12
+        bf16_peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
+        tf32_peak = (bf16_peak / 2.0) if bf16_peak else 1125.0
+        tmem_peak = r1.tmem_read_peak(local_rank, 16) * sm_count               # bytes/s, measured live (16 warps per SM)
+        tmem_bps = tests * 4 / (ms_trace * 1e-3)
+        roofline["note"] = ("frac > 1 is not an error: the filter (8 of the reference's 10 FMA-pipe instructions per test) runs as a split-TF32 "
+                            "GEMM on the tensor cores; see `tensor` and `tmem_read` for the hardware bounds of this kernel")
+        roofline["tensor"] = {"executed": tf32_exec, "peak": tf32_peak, "unit": "TFLOP/s", "frac": tf32_exec / tf32_peak,
+                              "peak_source": "MEASURED_PEAKS.json sustained dense bf16 / 2" if bf16_peak else "nominal dense TF32 (half of 2.25 PFLOP/s bf16)",
+                              "flops_model": "2 x K = 32 (11 lifted features x {hi hi, lo hi, hi lo}) per ray-sphere test, %d columns per ray" % n32}
+        roofline["tmem_read"] = {"achieved": tmem_bps / 1e12, "peak": tmem_peak / 1e12, "unit": "TB/s", "frac": tmem_bps / tmem_peak,
+                                 "peak_source": "tcgen05.ld 32x32b.x32 microbenchmark on this GPU (r1_tmem_read_peak, 16 warps per SM)",
+                                 "bytes_model": "4 bytes per ray-sphere test (one FP32 accumulator column)"}
 
     line = {"metric": metric_name(args.workload), "value": total_rays / (ms_value * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "strong",

@@ -36,7 +36,9 @@ enum { R1_MAT_NONE = -1, R1_MAT_LAMBERT = 0, R1_MAT_METAL = 1, R1_MAT_DIELECTRIC
 
 /* Kernel variants measured against each other (north_star (2)). */
 enum {
-    R1_VARIANT_MEGAKERNEL = 0, /* persistent threads, per-lane path state machine, per-lane packed f32x2 scan (fastest; default) */
+    R1_VARIANT_MEGAKERNEL = 0, /* default: the fastest megakernel for the scene -- R1_VARIANT_MEGAKERNEL_TENSOR for scan-heavy scenes
+                                  that fit its shared-memory operand (256 .. 768 spheres), R1_VARIANT_MEGAKERNEL_PACKED otherwise
+                                  (and whenever blocks_per_sm / threads are given: they tune the packed kernel) */
     R1_VARIANT_WAVEFRONT = 1,  /* generate / intersect / shade kernels over compacted ray queues, CUDA-graph WHILE loop */
     R1_VARIANT_MEGAKERNEL_SCALAR = 2, /* A/B: megakernel with a per-lane scalar FFMA scan */
     R1_VARIANT_MEGAKERNEL_COOP = 3,   /* A/B: megakernel with the warp-cooperative scan (quads share sphere loads, candidates
@@ -44,8 +46,10 @@ enum {
     R1_VARIANT_MEGAKERNEL_DEFERRED = 4, /* A/B: per-lane packed scan, candidates deferred to a per-warp queue and resolved once per
                                          scan with every lane busy */
     R1_VARIANT_MEGAKERNEL_DUAL = 5,    /* A/B: two paths per lane share every sphere load (768 threads x 80 registers) */
-    R1_VARIANT_MEGAKERNEL_TENSOR = 6   /* the filter as a TF32 GEMM on the tensor cores (tcgen05.mma, accumulators in TMEM), 128 rays x 64
-                                         spheres per instruction; scenes of up to 768 spheres */
+    R1_VARIANT_MEGAKERNEL_TENSOR = 6,  /* persistent threads, per-lane path state machine, the filter as a split-TF32 GEMM on the tensor
+                                         cores (tcgen05.mma, accumulators in TMEM), 128 rays x 64 spheres per instruction; scenes of up
+                                         to 768 spheres */
+    R1_VARIANT_MEGAKERNEL_PACKED = 7   /* persistent threads, per-lane path state machine, per-lane packed f32x2 (FFMA2) filter */
 };
 
 typedef struct r1_scene r1_scene; /* opaque: host SoA + per-device buffers */
@@ -139,6 +143,9 @@ int r1_deinterleave_rows(int device, const void *d_gathered, uint64_t stride, vo
 /* Hitable::hit (rayweek1.cpp:152-339); index = -1 on a miss.  dir must be unit length (Ray ctor, :104-108). */
 int r1_trace_rays(r1_scene *scene, int n, const float *org, const float *dir, float t_min, float t_max, int variant,
                   int32_t *index, float *t, float *p, float *normal);
+/* Name of the trace kernel `variant` resolves to for this scene with default tuning ("megakernel_tc2", "megakernel_pool", ...);
+ * static storage. */
+const char *r1_kernel_name(r1_scene *scene, int variant);
 /* Values of the tensor-core FILTER (R1_VARIANT_MEGAKERNEL_TENSOR) for n rays against every sphere: e[ray * n32 + sphere], n32 =
  * sphere count padded to 32; the filter flags a sphere iff the sign bit of e is clear, and must flag every sphere Hitable::hit's
  * discriminant test (rayweek1.cpp:192-204) accepts.  layout = 0. */
@@ -162,6 +169,9 @@ int r1_rng_draws(uint32_t pixel, uint32_t sample, uint32_t seed, int n, uint32_t
  * cross-check only -- on the B200 boxes of this project clock64 did not tick at the SM clock (it read ~300 MHz while
  * nvidia-smi showed 1965 MHz under the same load), so bench.py reports the nvidia-smi clock instead. */
 int r1_fma_peak(int device, int packed, double *tflops, double *sm_mhz_est);
+/* TMEM read throughput microbenchmark: `warps` warps per SM (1 CTA per SM) each read 32 lanes x 32 columns per tcgen05.ld.
+ * Returns bytes per second per SM -- the bound of the tensor-core filter (4 bytes per ray-sphere test leave TMEM). */
+int r1_tmem_read_peak(int device, int warps, double *bytes_per_second_per_sm);
 
 /* ---- part 2: the reference's host surface, C linkage ------------------------------------------------------------- */
 

@@ -15,9 +15,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("R1_LIBRARY") or os.path.join(_HERE, "librays1_b200.so")   # R1_LIBRARY: an alternative build, for A/B runs
 EXE_PATH = os.path.join(_HERE, "rays1_b200")
 
-VARIANT_MEGAKERNEL, VARIANT_WAVEFRONT, VARIANT_MEGAKERNEL_SCALAR, VARIANT_MEGAKERNEL_COOP, VARIANT_MEGAKERNEL_DEFERRED, VARIANT_MEGAKERNEL_DUAL, VARIANT_MEGAKERNEL_TENSOR = 0, 1, 2, 3, 4, 5, 6
+VARIANT_MEGAKERNEL, VARIANT_WAVEFRONT, VARIANT_MEGAKERNEL_SCALAR, VARIANT_MEGAKERNEL_COOP, VARIANT_MEGAKERNEL_DEFERRED, VARIANT_MEGAKERNEL_DUAL, VARIANT_MEGAKERNEL_TENSOR, VARIANT_MEGAKERNEL_PACKED = 0, 1, 2, 3, 4, 5, 6, 7
 VARIANTS = {"mega": VARIANT_MEGAKERNEL, "wavefront": VARIANT_WAVEFRONT, "scalar": VARIANT_MEGAKERNEL_SCALAR, "coop": VARIANT_MEGAKERNEL_COOP,
-            "deferred": VARIANT_MEGAKERNEL_DEFERRED, "dual": VARIANT_MEGAKERNEL_DUAL, "tensor": VARIANT_MEGAKERNEL_TENSOR}
+            "deferred": VARIANT_MEGAKERNEL_DEFERRED, "dual": VARIANT_MEGAKERNEL_DUAL, "tensor": VARIANT_MEGAKERNEL_TENSOR, "packed": VARIANT_MEGAKERNEL_PACKED}
 MAT_NONE, MAT_LAMBERT, MAT_METAL, MAT_DIELECTRIC = -1, 0, 1, 2
 
 # the reference's compile-time workload (src/common/common.h:18-25)
@@ -83,6 +83,8 @@ def _load():
         "r1_replay_pixels": (ci, [vp, ci, i32p, ci, ci, ci, ci, u32p, u32p, f32p, u32p]),
         "r1_rng_draws": (ci, [C.c_uint32, C.c_uint32, C.c_uint32, ci, u32p]),
         "r1_fma_peak": (ci, [ci, ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+        "r1_tmem_read_peak": (ci, [ci, ci, C.POINTER(C.c_double)]),
+        "r1_kernel_name": (C.c_char_p, [vp, ci]),
         "r1_host_configure": (ci, [ci, ci, ci, ci, ci, ci, C.c_uint32]),
         "r1_host_set_quiet": (ci, [ci]),
         "r1_host_create_scene": (vp, [C.c_char_p, ci]),
@@ -349,6 +351,13 @@ def fma_peak(device=0, packed=False):
     tf, mhz = C.c_double(0), C.c_double(0)
     _check(lib.r1_fma_peak(device, 1 if packed else 0, C.byref(tf), C.byref(mhz)), "r1_fma_peak")
     return tf.value, mhz.value
+
+
+def tmem_read_peak(device=0, warps=16):
+    """TMEM read throughput microbenchmark -> bytes per second per SM."""
+    v = C.c_double(0)
+    _check(lib.r1_tmem_read_peak(device, warps, C.byref(v)), "r1_tmem_read_peak")
+    return v.value
 
 
 def local_rows(height, row_tile, rank, world):

@@ -263,10 +263,10 @@ int launch_megakernel_dual(int sm_count, const r1::RenderArgs &args, const r1_re
 
 // tensor-core filter (r1::megakernel_tc, R1_VARIANT_MEGAKERNEL_TENSOR): `threads` selects the number of 128-ray groups per CTA,
 // R1_TC_CFG="chunk,buffers" the TMEM pipeline (columns per accumulator buffer, buffers per group; groups x buffers x chunk <= 512)
-template <int kGroups, int kChunk, int kBufs>
+template <int kGroups, int kChunk, int kBufs, bool kATmem>
 int launch_megakernel_tc_t(int sm_count, const r1::RenderArgs &args, cudaStream_t stream)
 {
-    auto kern = r1::megakernel_tc<kGroups, kChunk, kBufs>;
+    auto kern = r1::megakernel_tc<kGroups, kChunk, kBufs, kATmem>;
     const size_t smem = r1::tc_smem_bytes(kGroups, args.scene.n32);
     R1_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = sm_count;                                         // one CTA per SM: it owns all 512 TMEM columns
@@ -277,18 +277,42 @@ int launch_megakernel_tc_t(int sm_count, const r1::RenderArgs &args, cudaStream_
     return R1_OK;
 }
 
+template <int kGroups, int kChunk>
+int launch_megakernel_tc2_t(int sm_count, const r1::RenderArgs &args, cudaStream_t stream)
+{
+    auto kern = r1::megakernel_tc2<kGroups, kChunk>;
+    const size_t smem = r1::tc2_smem_bytes(kGroups, args.scene.n32);
+    if (smem > 227 * 1024) return fail(R1_ERR_LIMIT, "tensor variant: %d ray groups need %zu bytes of shared memory for this scene", kGroups, smem);
+    R1_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = sm_count;
+    const unsigned long long max_ctas = (args.n_samples + kGroups * 128 - 1) / (kGroups * 128);
+    if ((unsigned long long)grid > max_ctas) grid = (int)std::max<unsigned long long>(1, max_ctas);
+    kern<<<grid, kGroups * 128, smem, stream>>>(args);
+    R1_CUDA(cudaGetLastError());
+    return R1_OK;
+}
+
 int launch_megakernel_tc(int sm_count, const r1::RenderArgs &args, const r1_render_params &prm, cudaStream_t stream)
 {
     if (!args.scene.tcb) return fail(R1_ERR_LIMIT, "the tensor-core filter keeps at most %d spheres in shared memory", r1::tc::kMaxSpheres);
-    const int threads = prm.threads > 0 ? prm.threads : 512;
-    int chunk = 64, bufs = 2;
-    if (const char *e = getenv("R1_TC_CFG")) sscanf(e, "%d,%d", &chunk, &bufs);
-#define R1_TC_CASE(G, C, B) if (threads == G * 128 && chunk == C && bufs == B) return launch_megakernel_tc_t<G, C, B>(sm_count, args, stream)
-    R1_TC_CASE(4, 64, 2); R1_TC_CASE(4, 32, 4); R1_TC_CASE(4, 128, 1); R1_TC_CASE(4, 32, 2); R1_TC_CASE(4, 32, 3);
-    R1_TC_CASE(3, 64, 2); R1_TC_CASE(3, 32, 4);
-    R1_TC_CASE(2, 64, 2); R1_TC_CASE(2, 128, 2); R1_TC_CASE(2, 64, 4);
+    if (!getenv("R1_TC1")) {   // r1::megakernel_tc2 (default): the last ray warp to arrive issues the MMA; R1_TC2 = ray groups per CTA
+        const int groups = getenv("R1_TC2") ? atoi(getenv("R1_TC2")) : (prm.threads > 0 ? prm.threads / 128 : 4);
+        if (groups == 4) return launch_megakernel_tc2_t<4, 128>(sm_count, args, stream);
+        if (groups == 5) return launch_megakernel_tc2_t<5, 96>(sm_count, args, stream);
+        if (groups == 6) return launch_megakernel_tc2_t<6, 64>(sm_count, args, stream);
+        if (groups == 7) return launch_megakernel_tc2_t<7, 64>(sm_count, args, stream);
+        return fail(R1_ERR_ARG, "the tensor variant runs 4 .. 7 groups of 128 ray threads per CTA (threads = 512 .. 896)");
+    }
+    // R1_TC1=1: r1::megakernel_tc, one MMA-issuing warp per group (A/B)
+    const int threads = prm.threads > 0 ? prm.threads : (getenv("R1_TC_THREADS") ? atoi(getenv("R1_TC_THREADS")) : 512);
+    int chunk = 128, bufs = 1, atmem = 0;
+    if (const char *e = getenv("R1_TC_CFG")) sscanf(e, "%d,%d,%d", &chunk, &bufs, &atmem);
+#define R1_TC_CASE(G, C, B, A) if (threads == G * 128 && chunk == C && bufs == B && atmem == A) return launch_megakernel_tc_t<G, C, B, A != 0>(sm_count, args, stream)
+    R1_TC_CASE(4, 128, 1, 0); R1_TC_CASE(4, 64, 2, 0); R1_TC_CASE(4, 96, 1, 1); R1_TC_CASE(4, 32, 3, 1);
+    R1_TC_CASE(3, 128, 1, 0); R1_TC_CASE(3, 64, 2, 0); R1_TC_CASE(3, 128, 1, 1); R1_TC_CASE(3, 64, 2, 1);
+    R1_TC_CASE(2, 128, 2, 0); R1_TC_CASE(2, 256, 1, 0); R1_TC_CASE(2, 96, 2, 1); R1_TC_CASE(2, 224, 1, 1);
 #undef R1_TC_CASE
-    return fail(R1_ERR_ARG, "tensor variant: no kernel for %d ray threads, chunk %d, %d buffers", threads, chunk, bufs);
+    return fail(R1_ERR_ARG, "tensor variant: no kernel for %d ray threads, chunk %d, %d buffers, A in %s", threads, chunk, bufs, atmem ? "TMEM" : "shared memory");
 }
 
 template <int kScan, bool kStaged, int kThreads>
@@ -309,6 +333,18 @@ int launch_megakernel(int sm_count, const r1::RenderArgs &args, const r1_render_
     return fail(R1_ERR_ARG, "threads must be 512, 768 or 1024 (got %d)", threads);
 }
 
+// R1_VARIANT_MEGAKERNEL = the fastest megakernel for the scene.  Measured on B200: the tensor-core filter wins on the large scene
+// (485 spheres: 10.2 against 6.2 G rays/s) and loses where a scan is short (medium, 58 spheres: 25 against 34 G).  Explicit
+// tuning knobs (blocks_per_sm, threads, R1_POOL=0) address the packed kernel; R1_AUTO_TENSOR=0 keeps it everywhere.
+int resolve_variant(const r1::DevScene &dev, const r1_render_params &prm)
+{
+    if (prm.variant != R1_VARIANT_MEGAKERNEL) return prm.variant;
+    const bool tuned = prm.blocks_per_sm > 0 || prm.threads > 0 || (getenv("R1_POOL") && atoi(getenv("R1_POOL")) == 0) || getenv("R1_FORCE_UNSTAGED");
+    const bool off = getenv("R1_AUTO_TENSOR") && atoi(getenv("R1_AUTO_TENSOR")) == 0;
+    if (dev.tcb && dev.n8 >= 256 && !tuned && !off) return R1_VARIANT_MEGAKERNEL_TENSOR;
+    return R1_VARIANT_MEGAKERNEL_PACKED;
+}
+
 int validate(const r1_render_params *p)
 {
     if (!p) return fail(R1_ERR_ARG, "null params");
@@ -318,7 +354,7 @@ int validate(const r1_render_params *p)
     // the pixel accumulators hold sums of radiance * 2^24 in 64 bits, one sample saturating at 2^32 - 1 (r1_kernels.cuh): 2^20
     // samples per pixel cannot wrap them
     if (p->spp > (1 << 20)) return fail(R1_ERR_LIMIT, "spp %d exceeds the accumulator limit of 2^20 samples per pixel", p->spp);
-    if (p->variant < 0 || p->variant > 6) return fail(R1_ERR_ARG, "unknown variant %d", p->variant);
+    if (p->variant < 0 || p->variant > 7) return fail(R1_ERR_ARG, "unknown variant %d", p->variant);
     return R1_OK;
 }
 
@@ -614,6 +650,7 @@ int r1_render_device(r1_scene *scene, const r1_render_params *params, void *d_rg
     const bool pool_sched = !(getenv("R1_POOL") && atoi(getenv("R1_POOL")) == 0);
     if (c.dev.n8 >= 256) { a.sched_kmax = pool_sched ? 8 : 1; a.sched_div = pool_sched ? 16 : 1; }
     else { a.sched_kmax = 64; a.sched_div = 16; }
+    a.tc_flags = getenv("R1_TC_FLAGS") ? (uint32_t)atoi(getenv("R1_TC_FLAGS")) : 1u;
     if (const char *e = getenv("R1_SCHED")) {  // tuning knob: "kmax,div"
         unsigned k = 0, d = 0;
         if (sscanf(e, "%u,%u", &k, &d) == 2 && k >= 1 && k <= 4096 && d >= 1 && d <= 1024) { a.sched_kmax = k; a.sched_div = d; }
@@ -643,21 +680,22 @@ int r1_render_device(r1_scene *scene, const r1_render_params *params, void *d_rg
         // scenes of up to 4096 spheres are staged in shared memory; R1_FORCE_UNSTAGED=1 exercises the global-memory path on small scenes
         const bool staged = c.dev.n_pad <= r1::kMaxStagedSpheres && !getenv("R1_FORCE_UNSTAGED");
         R1_CUDA(cudaEventRecord(x.ev[1], stream));
-        if (prm.variant == R1_VARIANT_WAVEFRONT) {
+        const int variant = resolve_variant(c.dev, prm);
+        if (variant == R1_VARIANT_WAVEFRONT) {
             if (c.dev.n_pad > r1::kMaxStagedSpheres) return fail(R1_ERR_LIMIT, "the wavefront variant stages at most %d spheres", r1::kMaxStagedSpheres);
             uint32_t launches = 0;
             rc = r1::wavefront_render(x.wf, a, x.sm_count, stream, &launches);
             if (rc) return fail(R1_ERR_CUDA, "wavefront: %s", cudaGetErrorString((cudaError_t)rc));
             x.last_launches += launches;
         } else {
-            if (prm.variant == R1_VARIANT_MEGAKERNEL) rc = staged ? launch_megakernel<r1::kScanLanePacked, true>(x.sm_count, a, prm, stream)
+            if (variant == R1_VARIANT_MEGAKERNEL_PACKED) rc = staged ? launch_megakernel<r1::kScanLanePacked, true>(x.sm_count, a, prm, stream)
                                                                   : launch_megakernel<r1::kScanLanePacked, false>(x.sm_count, a, prm, stream);
-            else if (prm.variant == R1_VARIANT_MEGAKERNEL_COOP) rc = staged ? launch_megakernel<r1::kScanCoop, true>(x.sm_count, a, prm, stream)
+            else if (variant == R1_VARIANT_MEGAKERNEL_COOP) rc = staged ? launch_megakernel<r1::kScanCoop, true>(x.sm_count, a, prm, stream)
                                                                             : launch_megakernel<r1::kScanCoop, false>(x.sm_count, a, prm, stream);
-            else if (prm.variant == R1_VARIANT_MEGAKERNEL_DEFERRED) rc = staged ? launch_megakernel<r1::kScanLaneDeferred, true>(x.sm_count, a, prm, stream)
+            else if (variant == R1_VARIANT_MEGAKERNEL_DEFERRED) rc = staged ? launch_megakernel<r1::kScanLaneDeferred, true>(x.sm_count, a, prm, stream)
                                                                                 : launch_megakernel<r1::kScanLaneDeferred, false>(x.sm_count, a, prm, stream);
-            else if (prm.variant == R1_VARIANT_MEGAKERNEL_TENSOR) rc = launch_megakernel_tc(x.sm_count, a, prm, stream);
-            else if (prm.variant == R1_VARIANT_MEGAKERNEL_DUAL) rc = staged ? launch_megakernel_dual<true>(x.sm_count, a, prm, stream)
+            else if (variant == R1_VARIANT_MEGAKERNEL_TENSOR) rc = launch_megakernel_tc(x.sm_count, a, prm, stream);
+            else if (variant == R1_VARIANT_MEGAKERNEL_DUAL) rc = staged ? launch_megakernel_dual<true>(x.sm_count, a, prm, stream)
                                                                             : launch_megakernel_dual<false>(x.sm_count, a, prm, stream);
             else rc = staged ? launch_megakernel<r1::kScanLaneScalar, true>(x.sm_count, a, prm, stream)
                              : launch_megakernel<r1::kScanLaneScalar, false>(x.sm_count, a, prm, stream);
@@ -798,6 +836,21 @@ int r1_trace_rays(r1_scene *scene, int n, const float *org, const float *dir, fl
     return R1_OK;
 }
 
+const char *r1_kernel_name(r1_scene *scene, int variant)
+{
+    DeviceCtx *cp = nullptr;
+    if (get_ctx(scene, &cp)) return "";
+    r1_render_params prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.variant = variant;
+    switch (resolve_variant(cp->dev, prm)) {
+    case R1_VARIANT_WAVEFRONT: return "wf_intersect + wf_shade (graph loop)";
+    case R1_VARIANT_MEGAKERNEL_TENSOR: return getenv("R1_TC1") ? "megakernel_tc" : "megakernel_tc2";
+    case R1_VARIANT_MEGAKERNEL_DUAL: return "megakernel_pool2";
+    default: return (getenv("R1_POOL") && atoi(getenv("R1_POOL")) == 0) ? "megakernel" : "megakernel_pool";
+    }
+}
+
 int r1_filter_probe(r1_scene *scene, int n, const float *org, const float *dir, int layout, float *e)
 {
     DeviceCtx *cp = nullptr;
@@ -809,7 +862,7 @@ int r1_filter_probe(r1_scene *scene, int n, const float *org, const float *dir, 
     DevBuf d_org, d_dir, d_e;
     R1_TRY(d_org.upload(org, (size_t)n * 12)); R1_TRY(d_dir.upload(dir, (size_t)n * 12));
     R1_TRY(d_e.alloc((size_t)n * n32 * 4));
-    const size_t smem = 256 + (size_t)n32 * r1::tc::kRowBytes + 128 * r1::tc::kRowBytes;
+    const size_t smem = ((sizeof(r1::TcControl) + 127) & ~(size_t)127) + (size_t)n32 * r1::tc::kRowBytes + 128 * r1::tc::kRowBytes;
     R1_CUDA(cudaFuncSetAttribute(r1::tc_filter_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // layout 1 swaps the two stride fields of the shared-memory descriptors (bring-up aid; 0 is the layout the renderer uses)
     const uint32_t lbo = layout == 1 ? r1::tc::kSBO : r1::tc::kLBO, sbo = layout == 1 ? r1::tc::kLBO : r1::tc::kSBO;
@@ -887,6 +940,30 @@ int r1_rng_draws(uint32_t pixel, uint32_t sample, uint32_t seed, int n, uint32_t
     R1_CUDA(cudaGetLastError());
     R1_CUDA(cudaDeviceSynchronize());
     R1_TRY(d.download(out, (size_t)n * 4));
+    return R1_OK;
+}
+
+int r1_tmem_read_peak(int device, int warps, double *bytes_per_second_per_sm)
+{
+    if (!bytes_per_second_per_sm || warps < 1 || warps > 32) return fail(R1_ERR_ARG, "bad argument");
+    R1_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    R1_CUDA(cudaGetDeviceProperties(&prop, device));
+    DevBuf sink;
+    R1_TRY(sink.alloc(16));
+    cudaEvent_t e0, e1;
+    R1_CUDA(cudaEventCreate(&e0)); R1_CUDA(cudaEventCreate(&e1));
+    const int iters = 20000;
+    r1::tmem_read_kernel<<<prop.multiProcessorCount, warps * 32>>>(100, sink.as<uint32_t>());   // warm-up
+    R1_CUDA(cudaEventRecord(e0));
+    r1::tmem_read_kernel<<<prop.multiProcessorCount, warps * 32>>>(iters, sink.as<uint32_t>());
+    R1_CUDA(cudaEventRecord(e1));
+    R1_CUDA(cudaEventSynchronize(e1));
+    R1_CUDA(cudaGetLastError());
+    float ms = 0;
+    R1_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *bytes_per_second_per_sm = (double)warps * iters * 4096.0 / (ms * 1e-3);
     return R1_OK;
 }
 

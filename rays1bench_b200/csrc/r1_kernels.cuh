@@ -30,6 +30,7 @@ struct RenderArgs {
     float inv_w, inv_h, inv_spp;
     uint64_t seed;                   // Rng::seed_hash(global seed)
     uint64_t magic_chunks, magic_width, magic_row_tile;  // floor(2^64 / d) + 1: exact n / d for 32-bit n via one 64-bit mul-high (0 when d == 1)
+    uint32_t tc_flags;                   // megakernel_tc experiments (R1_TC_FLAGS): 1 = mbarrier waits suspend, 2 = one funnel-shift chain
     uint32_t sched_kmax, sched_div;      // guided self-scheduling: min(kmax, max(1, left / (lanes * div))) units per lane (megakernel) or
                                          // x 32 samples per warp (megakernel_pool) per atomic
     // sample-pool scheduling (megakernel_pool): work items are single samples g = lp * spp + s, handed out 32 at a time
@@ -701,12 +702,15 @@ constexpr size_t tc_smem_bytes(int groups, int n32)
            (size_t)groups * 4 * sizeof(WarpPool) + 128;          // + alignment slack
 }
 
-template <int kGroups, int kChunk, int kBufs>
+template <int kGroups, int kChunk, int kBufs, bool kATmem>
 __global__ void __launch_bounds__(kGroups * 160, 1) megakernel_tc(const __grid_constant__ RenderArgs a)
 {
     static_assert(kGroups >= 1 && kGroups <= 4 && kBufs >= 1 && kBufs <= 4 && kChunk % 32 == 0 && kChunk <= 256, "bad configuration");
-    static_assert(kGroups * kBufs * kChunk <= 512, "TMEM has 512 columns");
+    // TMEM columns of group g: [g * kGroupCols, +32) = the ray operand if kATmem, then kBufs accumulator buffers of kChunk columns
+    constexpr int kGroupCols = (512 / kGroups) & ~31, kDCol = kATmem ? 32 : 0;
+    static_assert(kDCol + kBufs * kChunk <= kGroupCols, "TMEM has 512 columns");
     constexpr int kPieces = kChunk / 32;
+    const bool hint = a.tc_flags & 1u, one_chain = a.tc_flags & 2u;
     constexpr int kRayThreads = kGroups * 128;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // shared memory: [16 B | rsqrtss table 4 KB | control | B tile n32 x 128 B | exact n32 x 16 B | A tiles kGroups x 16 KB | pools]
@@ -754,7 +758,7 @@ __global__ void __launch_bounds__(kGroups * 160, 1) megakernel_tc(const __grid_c
             const uint32_t a_smem = tc::smem_u32(s_a + (size_t)g * 128 * tc::kRowBytes), b_smem = tc::smem_u32(s_b);
             uint32_t it = 0;
             for (uint32_t scan_no = 0;; ++scan_no) {
-                tc::mbar_wait(&ctl.a_full[g], scan_no & 1u);
+                tc::mbar_wait(&ctl.a_full[g], scan_no & 1u, hint);
                 const volatile uint32_t *dn = ctl.done[g];
                 if (dn[0] && dn[1] && dn[2] && dn[3]) {          // nobody has a path left: wake the group up and leave
                     *reinterpret_cast<volatile uint32_t *>(&ctl.exit_flag[g]) = 1u;
@@ -764,10 +768,12 @@ __global__ void __launch_bounds__(kGroups * 160, 1) megakernel_tc(const __grid_c
                 tc::tc_fence_after();
                 for (int c = 0; c < nchunks; ++c, ++it) {
                     const uint32_t b = it % kBufs;
-                    tc::mbar_wait(&ctl.empty[g][b], ((it / kBufs) & 1u) ^ 1u);
+                    tc::mbar_wait(&ctl.empty[g][b], ((it / kBufs) & 1u) ^ 1u, hint);
                     tc::tc_fence_after();
                     const int n = min(kChunk, n32 - c * kChunk);
-                    tc::mma_chunk(tmem_base + (uint32_t)(g * kBufs + (int)b) * kChunk, a_smem, b_smem + (uint32_t)c * (kChunk / 8) * tc::kSBO, n, tc::kLBO, tc::kSBO);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(g * kGroupCols + kDCol + (int)b * kChunk);
+                    if (kATmem) tc::mma_chunk_ts(d_tmem, tmem_base + (uint32_t)(g * kGroupCols), b_smem + (uint32_t)c * (kChunk / 8) * tc::kSBO, n);
+                    else tc::mma_chunk(d_tmem, a_smem, b_smem + (uint32_t)c * (kChunk / 8) * tc::kSBO, n, tc::kLBO, tc::kSBO);
                     tc::mma_commit(&ctl.full[g][b]);
                 }
             }
@@ -779,7 +785,7 @@ __global__ void __launch_bounds__(kGroups * 160, 1) megakernel_tc(const __grid_c
         const unsigned lt_mask = (1u << lane) - 1u;
         WarpPool &pool = pools[threadIdx.x >> 5];
         unsigned char *a_tile = s_a + (size_t)g * 128 * tc::kRowBytes;
-        const uint32_t t_lane = tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(g * kBufs) * kChunk;
+        const uint32_t t_row = tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(g * kGroupCols), t_lane = t_row + kDCol;
         bool active = false, exhausted = false;
         PoolState ps;
         ps.dry = false; ps.ready = 0; ps.w_next = 0; ps.w_end = 0;
@@ -796,8 +802,15 @@ __global__ void __launch_bounds__(kGroups * 160, 1) megakernel_tc(const __grid_c
             if (need) pool_take(a, pool, ps, tab, lane, lt_mask, lanes_x, need, want, active, exhausted, o, d, lp, rng, thr, depth);
             const bool warp_done = __all_sync(kFull, exhausted);
 
-            tc::write_ray_row(a_tile, r, o, d, active);
-            tc::fence_proxy_async();
+            if (kATmem) {
+                uint32_t row[tc::kK];
+                tc::ray_row(o, d, active, row);
+                tc::tmem_st32(t_row, row);
+                tc::tc_fence_before();
+            } else {
+                tc::write_ray_row(a_tile, r, o, d, active);
+                tc::fence_proxy_async();
+            }
             __syncwarp();
             if (lane == 0) {
                 *reinterpret_cast<volatile uint32_t *>(&ctl.done[g][w]) = warp_done ? 1u : 0u;
@@ -809,7 +822,7 @@ __global__ void __launch_bounds__(kGroups * 160, 1) megakernel_tc(const __grid_c
             bool leave = false;
             for (int c = 0; c < nchunks; ++c, ++it) {
                 const uint32_t b = it % kBufs;
-                tc::mbar_wait(&ctl.full[g][b], (it / kBufs) & 1u);
+                tc::mbar_wait(&ctl.full[g][b], (it / kBufs) & 1u, hint);
                 if (c == 0 && *reinterpret_cast<volatile uint32_t *>(&ctl.exit_flag[g])) { leave = true; break; }
                 tc::tc_fence_after();
                 const int pieces = min(kPieces, (n32 - c * kChunk) >> 5);   // warp-uniform: the last chunk may be short
@@ -820,7 +833,7 @@ __global__ void __launch_bounds__(kGroups * 160, 1) megakernel_tc(const __grid_c
                     if (h < pieces) {
                         uint32_t v[32];
                         tc::tmem_ld32(t_lane + b * kChunk + 32 * h, v);
-                        cand[h] = tc::flagged(v);
+                        cand[h] = one_chain ? tc::flagged_chain(v) : tc::flagged(v);
                     }
                 }
                 tc::tc_fence_before();
@@ -850,6 +863,209 @@ __global__ void __launch_bounds__(kGroups * 160, 1) megakernel_tc(const __grid_c
     tc::tc_fence_before();
     __syncthreads();
     if (threadIdx.x < 32) tc::tmem_dealloc(tmem_base, 512);
+}
+
+// megakernel_tc without issuing warps: the LAST ray warp of a group to arrive -- with its row written (first chunk of a scan) or
+// with its 32 lanes of the accumulator buffer read (next chunk) -- issues the tcgen05.mma itself.  Arrivals are counted in shared
+// memory (atomicAdd); nobody has to be woken up to issue, no warp spins on behalf of others, and a CTA holds up to 7 groups
+// (896 threads), each with ONE accumulator buffer of kChunk columns.
+struct TcControl2 {
+    uint64_t full[8];                 // per group: accumulator chunk complete (tcgen05.commit; the exit arrival), count 1
+    uint32_t arrived_a[8];            // per group: ray warps with their row written (low byte) / out of work (next byte)
+    uint32_t arrived_e[8];            // per group: ray warps that have read the current chunk
+    uint32_t exit_flag[8];
+    uint32_t tmem_base;
+    uint32_t pad_[7];
+};
+static_assert(sizeof(TcControl2) % 16 == 0, "TcControl2 is followed by 16-byte aligned tiles");
+
+constexpr size_t tc2_smem_bytes(int groups, int n32)
+{
+    return (size_t)kSmemSpheres + sizeof(TcControl2) + (size_t)n32 * tc::kRowBytes + (size_t)n32 * 16 + (size_t)groups * 128 * tc::kRowBytes +
+           (size_t)groups * 4 * sizeof(WarpPool) + 256;          // + alignment slack
+}
+
+template <int kGroups, int kChunk>
+__global__ void __launch_bounds__(kGroups * 128, 1) megakernel_tc2(const __grid_constant__ RenderArgs a)
+{
+    static_assert(kGroups >= 1 && kGroups <= 8 && kChunk % 32 == 0 && kChunk <= 256 && kGroups * kChunk <= 512, "bad configuration");
+    constexpr int kPieces = kChunk / 32;
+    const bool hint = a.tc_flags & 1u;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint16_t *s_tab = reinterpret_cast<uint16_t *>(smem_raw + 16);
+    unsigned char *p = smem_raw + ((kSmemSpheres + 127) & ~127);
+    TcControl2 &ctl = *reinterpret_cast<TcControl2 *>(p);
+    p += (sizeof(TcControl2) + 127) & ~127;
+    unsigned char *s_b = p;
+    const int n32 = a.scene.n32;
+    p += (size_t)n32 * tc::kRowBytes;
+    float4 *s_exact = reinterpret_cast<float4 *>(p);
+    p += (size_t)n32 * 16;
+    unsigned char *s_a = p;
+    p += (size_t)kGroups * 128 * tc::kRowBytes;
+    WarpPool *pools = reinterpret_cast<WarpPool *>(p);
+
+    for (int i = threadIdx.x; i < R1_RSQRT12_ENTRIES / 2; i += blockDim.x)
+        reinterpret_cast<uint32_t *>(s_tab)[i] = reinterpret_cast<const uint32_t *>(g_rsqrt12)[i];
+    for (int i = threadIdx.x; i < n32 * (tc::kRowBytes / 16); i += blockDim.x)
+        reinterpret_cast<uint4 *>(s_b)[i] = reinterpret_cast<const uint4 *>(a.scene.tcb)[i];
+    for (int i = threadIdx.x; i < n32; i += blockDim.x)
+        s_exact[i] = i < a.scene.n_pad ? a.scene.exact[i] : make_float4(0, 0, 0, 0);
+    if (threadIdx.x == 0) {
+        for (int g = 0; g < 8; ++g) {
+            tc::mbar_init(&ctl.full[g], 1);
+            ctl.arrived_a[g] = 0; ctl.arrived_e[g] = 0; ctl.exit_flag[g] = 0;
+        }
+        tc::fence_mbar_init();
+    }
+    tc::fence_proxy_async();                                     // the B tile is read by the tensor core (async proxy)
+    if (threadIdx.x < 32) tc::tmem_alloc(&ctl.tmem_base, 512);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(&ctl.tmem_base);
+    const int nchunks = (n32 + kChunk - 1) / kChunk;
+    const unsigned lane = threadIdx.x & 31u;
+    const int g = threadIdx.x >> 7, w = (threadIdx.x >> 5) & 3, r = threadIdx.x & 127;
+    const uint16_t *tab = s_tab;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    WarpPool &pool = pools[threadIdx.x >> 5];
+    unsigned char *a_tile = s_a + (size_t)g * 128 * tc::kRowBytes;
+    const uint32_t a_smem = tc::smem_u32(a_tile), b_smem = tc::smem_u32(s_b);
+    const uint32_t d_tmem = tmem_base + (uint32_t)(g * kChunk), t_lane = d_tmem + ((uint32_t)(w * 32) << 16);
+    bool active = false, exhausted = false;
+    PoolState ps;
+    ps.dry = false; ps.ready = 0; ps.w_next = 0; ps.w_end = 0;
+    const uint32_t lanes_x = gridDim.x * blockDim.x * a.sched_div;
+    uint32_t lp = 0, it = 0, nrays = 0;
+    int depth = 0;
+    f3 thr = mk3(1, 1, 1), o = mk3(0, 0, 0), d = mk3(0, 0, 0);
+    Rng rng;
+    rng.k0 = 0; rng.k1 = 0;
+
+    for (;;) {
+        const bool want = !active && !exhausted;
+        const unsigned need = __ballot_sync(kFull, want);
+        if (need) pool_take(a, pool, ps, tab, lane, lt_mask, lanes_x, need, want, active, exhausted, o, d, lp, rng, thr, depth);
+        const bool warp_done = __all_sync(kFull, exhausted);
+
+        tc::write_ray_row(a_tile, r, o, d, active);
+        tc::fence_proxy_async();
+        tc::tc_fence_before();                                   // this warp's reads of the previous scan's last chunk are complete
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t mine = 1u + (warp_done ? 0x100u : 0u);
+            __threadfence_block();
+            const uint32_t tot = atomicAdd(&ctl.arrived_a[g], mine) + mine;
+            if ((tot & 0xffu) == 4u) {                           // last of the group: start the scan (or end the group)
+                *reinterpret_cast<volatile uint32_t *>(&ctl.arrived_a[g]) = 0u;
+                __threadfence_block();
+                if ((tot >> 8) == 4u) {
+                    *reinterpret_cast<volatile uint32_t *>(&ctl.exit_flag[g]) = 1u;
+                    __threadfence_block();
+                    tc::mbar_arrive(&ctl.full[g]);
+                } else {
+                    tc::tc_fence_after();
+                    tc::mma_chunk(d_tmem, a_smem, b_smem, min(kChunk, n32), tc::kLBO, tc::kSBO);
+                    tc::mma_commit(&ctl.full[g]);
+                }
+            }
+        }
+        __syncwarp();
+
+        float t = kTMax;
+        int hit = -1;
+        bool leave = false;
+        for (int c = 0; c < nchunks; ++c, ++it) {
+            tc::mbar_wait(&ctl.full[g], it & 1u, hint);
+            if (c == 0 && *reinterpret_cast<volatile uint32_t *>(&ctl.exit_flag[g])) { leave = true; break; }
+            tc::tc_fence_after();
+            const int pieces = min(kPieces, (n32 - c * kChunk) >> 5);   // warp-uniform: the last chunk may be short
+            uint32_t cand[kPieces + 1];
+#pragma unroll
+            for (int h = 0; h < kPieces; h += 2) {               // two loads in flight, eight independent sign-gather chains
+                cand[h] = 0; cand[h + 1] = 0;
+                if (kGroups <= 5 && h + 1 < pieces) {           // (6 and 7 groups have 72 .. 80 registers: one load at a time)
+                    uint32_t v0[32], v1[32];
+                    tc::tmem_ld32_issue(t_lane + 32 * h, v0);
+                    tc::tmem_ld32_issue(t_lane + 32 * h + 32, v1);
+                    tc::tmem_wait(v0, v1);
+                    cand[h] = tc::flagged(v0);
+                    cand[h + 1] = tc::flagged(v1);
+                } else {
+                    if (h < pieces) {
+                        uint32_t v[32];
+                        tc::tmem_ld32(t_lane + 32 * h, v);
+                        cand[h] = tc::flagged(v);
+                    }
+                    if (h + 1 < pieces) {
+                        uint32_t v[32];
+                        tc::tmem_ld32(t_lane + 32 * h + 32, v);
+                        cand[h + 1] = tc::flagged(v);
+                    }
+                }
+            }
+            if (c + 1 < nchunks) {                               // warp-uniform
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence_block();
+                    if (atomicAdd(&ctl.arrived_e[g], 1u) == 3u) {    // last reader: the buffer is free, issue the next chunk
+                        *reinterpret_cast<volatile uint32_t *>(&ctl.arrived_e[g]) = 0u;
+                        __threadfence_block();
+                        tc::tc_fence_after();
+                        tc::mma_chunk(d_tmem, a_smem, b_smem + (uint32_t)(c + 1) * (kChunk / 8) * tc::kSBO, min(kChunk, n32 - (c + 1) * kChunk), tc::kLBO, tc::kSBO);
+                        tc::mma_commit(&ctl.full[g]);
+                    }
+                }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int h = 0; h < kPieces; ++h)
+                if (cand[h]) exact_candidates(cand[h], s_exact, c * kChunk + 32 * h, o, d, kTMin, t, hit);
+        }
+        if (leave) break;
+
+        if (active) {
+            ++nrays;
+            f3 contrib;
+            const float4 e = hit >= 0 ? s_exact[hit] : make_float4(0, 0, 0, 0);
+            if (shade_step(a, hit, t, e, tab, o, d, thr, depth, rng, contrib)) {
+                accumulate_sample(a, lp, contrib);
+                active = false;
+            }
+        }
+    }
+    unsigned long long total = nrays;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(kFull, total, off);
+    if (lane == 0 && total) atomicAdd(a.num_rays, total);
+    tc::tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tc::tmem_dealloc(tmem_base, 512);
+}
+
+// TMEM read throughput: every warp reads 32 lanes x 32 columns (4 KB) per tcgen05.ld, `iters` times over its lane quarter's 512
+// columns.  Bounds the tensor-core filter: one 4-byte filter value per (ray, sphere) has to come out of TMEM.
+__global__ void __launch_bounds__(1024, 1) tmem_read_kernel(int iters, uint32_t *sink)
+{
+    __shared__ uint32_t slot;
+    if (threadIdx.x < 32) tc::tmem_alloc(&slot, 512);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t base = *reinterpret_cast<volatile uint32_t *>(&slot) + ((uint32_t)(((threadIdx.x >> 5) & 3) * 32) << 16);
+    uint32_t acc = 0;
+    for (int i = 0; i < iters; ++i) {
+        uint32_t v[32];
+        tc::tmem_ld32(base + (uint32_t)((i + (threadIdx.x >> 7)) & 15) * 32u, v);
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) acc ^= v[j];
+    }
+    if (acc == 0x12345678u) sink[0] = acc;                       // keeps the loads alive
+    tc::tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tc::tmem_dealloc(*reinterpret_cast<volatile uint32_t *>(&slot), 512);
 }
 
 // Filter values of n rays against every sphere (parity / error measurement of the tensor filter): e[ray * n32 + sphere].

@@ -79,12 +79,26 @@ __device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity)
     asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return done != 0;
 }
+__device__ __forceinline__ bool mbar_try_hint(uint64_t *bar, uint32_t parity, uint32_t ns)   // suspends up to `ns` before it reports failure
+{
+    uint32_t done;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done)
+                 : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+                 : "memory");
+    return done != 0;
+}
 // A barrier that never completes would hang the GPU; a protocol error traps instead (the launch then fails loudly).
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, bool hint = false)
 {
     uint32_t spins = 0;
-    while (!mbar_try(bar, parity))
-        if (++spins > (1u << 26)) __trap();
+    if (hint) {
+        while (!mbar_try_hint(bar, parity, 100000u))
+            if (++spins > (1u << 22)) __trap();
+    } else {
+        while (!mbar_try(bar, parity))
+            if (++spins > (1u << 26)) __trap();
+    }
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -112,6 +126,13 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64
                  "r"(idesc), "r"(accumulate)
                  : "memory");
 }
+// the same with the A operand in tensor memory (128 lanes x 8 columns per K step)
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc),
+                 "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint64_t *bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 
 // 32 consecutive columns of this thread's TMEM lane (warp w reads lanes 32 (w % 4) .. +31), complete on return
@@ -132,7 +153,41 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
                  :
                  : "memory");
 }
+// the same in two steps: issue (the registers are undefined until tmem_wait), and one wait for two loads in flight
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait(uint32_t (&a)[32], uint32_t (&b)[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]), "+r"(a[16]), "+r"(a[17]), "+r"(a[18]), "+r"(a[19]), "+r"(a[20]), "+r"(a[21]), "+r"(a[22]), "+r"(a[23]), "+r"(a[24]), "+r"(a[25]), "+r"(a[26]), "+r"(a[27]), "+r"(a[28]), "+r"(a[29]), "+r"(a[30]), "+r"(a[31]),
+                   "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]), "+r"(b[8]), "+r"(b[9]), "+r"(b[10]), "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15]), "+r"(b[16]), "+r"(b[17]), "+r"(b[18]), "+r"(b[19]), "+r"(b[20]), "+r"(b[21]), "+r"(b[22]), "+r"(b[23]), "+r"(b[24]), "+r"(b[25]), "+r"(b[26]), "+r"(b[27]), "+r"(b[28]), "+r"(b[29]), "+r"(b[30]), "+r"(b[31])
+                 :
+                 : "memory");
+}
+// 32 consecutive columns of this thread's TMEM lane, written (complete on return)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+                 "%24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+                 "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]),
+                 "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]),
+                 "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+                 : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 // sign bits of 32 filter values into a candidate mask: first sphere -> bit 31, set = flagged (e >= 0)
+__device__ __forceinline__ uint32_t flagged_chain(const uint32_t (&v)[32])      // one chain of 32 funnel shifts
+{
+    uint32_t neg = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) neg = __funnelshift_l(v[j], neg, 1);
+    return ~neg;
+}
 __device__ __forceinline__ uint32_t flagged(const uint32_t (&v)[32])
 {
     // four independent funnel-shift chains of 8 (one chain of 32 is a 32-deep dependency)
@@ -154,8 +209,8 @@ __device__ __forceinline__ uint32_t tf32_rna(float x)
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
 }
-// Row r of a 128-ray A tile.  Rays without a path (`live` false) get a row that flags nothing: e = -1e30.
-__device__ __forceinline__ void write_ray_row(unsigned char *a_tile, int r, f3 o, f3 d, bool live)
+// The lifted TF32 row of one ray.  Rays without a path (`live` false) get a row that flags nothing: e = -1e30.
+__device__ __forceinline__ void ray_row(f3 o, f3 d, bool live, uint32_t (&row)[kK])
 {
     float f[kFeatures];
     const float od = dot3(o, d);
@@ -169,7 +224,6 @@ __device__ __forceinline__ void write_ray_row(unsigned char *a_tile, int r, f3 o
         for (int j = 0; j < 9; ++j) f[j] = 0.0f;
         f[10] = -kPadKK;
     }
-    uint32_t row[kK];
 #pragma unroll
     for (int j = 0; j < kFeatures; ++j) {
         const uint32_t hi = tf32_rna(f[j]);
@@ -177,6 +231,12 @@ __device__ __forceinline__ void write_ray_row(unsigned char *a_tile, int r, f3 o
         row[kFeatures + j] = tf32_rna(fsub(f[j], __uint_as_float(hi)));
         if (j < kFeatures - 1) row[2 * kFeatures + j] = hi;
     }
+}
+// Row r of a 128-ray A tile in shared memory
+__device__ __forceinline__ void write_ray_row(unsigned char *a_tile, int r, f3 o, f3 d, bool live)
+{
+    uint32_t row[kK];
+    ray_row(o, d, live, row);
     unsigned char *base = a_tile + (uint32_t)(r >> 3) * kSBO + (uint32_t)(r & 7) * 16u;
 #pragma unroll
     for (int kc = 0; kc < kK / 4; ++kc)
@@ -190,6 +250,13 @@ __device__ __forceinline__ void mma_chunk(uint32_t d_tmem, uint32_t a_smem, uint
 #pragma unroll
     for (int k = 0; k < kK / 8; ++k)
         mma_tf32(d_tmem, smem_desc(a_smem + 2 * k * kLBO, lbo, sbo), smem_desc(b_smem + 2 * k * kLBO, lbo, sbo), idesc, k > 0);
+}
+// the same with A in tensor memory: row r = lane r, k = column a_tmem + k
+__device__ __forceinline__ void mma_chunk_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_smem, int n)
+{
+    const uint32_t idesc = instr_desc(n);
+#pragma unroll
+    for (int k = 0; k < kK / 8; ++k) mma_tf32_ts(d_tmem, a_tmem + 8 * k, smem_desc(b_smem + 2 * k * kLBO, kLBO, kSBO), idesc, k > 0);
 }
 #endif  // __CUDACC__
 

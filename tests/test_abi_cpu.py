@@ -105,7 +105,7 @@ def test_scene_abi_argument_checking(r1):
     assert lib.r1_render(sc, C.byref(p), np.zeros(16 * 9 * 3, np.uint8), C.byref(res)) == -1
     p.world, p.spp = 1, (1 << 20) + 1                                           # the 64-bit fixed-point pixel sums are sized for 2^20 samples
     assert lib.r1_render(sc, C.byref(p), np.zeros(16 * 9 * 3, np.uint8), C.byref(res)) == -4 and b"2^20" in lib.r1_last_error()
-    p.spp, p.variant = 1, 7
+    p.spp, p.variant = 1, 8
     assert lib.r1_render(sc, C.byref(p), np.zeros(16 * 9 * 3, np.uint8), C.byref(res)) == -1  # unknown variant
     assert lib.r1_scene_set_camera_raw(sc, np.zeros(22, np.float32)) == 0
     assert lib.r1_scene_commit(sc, 0) == -3 or lib.r1_device_count() > 0         # camera now set: the next obstacle is the missing GPU

@@ -175,20 +175,52 @@ def test_tensor_filter_is_conservative(r1, scenes, name):
     record("tensor_filter_flag_ratio_%s" % name, float(flagged.sum() / max(1, ((discr >= 0) & real[None, :]).sum())))
 
 
-def test_tensor_variant_renders_the_same_bytes(r1, scenes):
-    """same hits, same bytes: the tensor-core filter only decides which spheres get the exact test"""
+def test_tensor_variant_renders_the_same_bytes(r1, scenes, monkeypatch):
+    """same hits, same bytes: the tensor-core filter only decides which spheres get the exact test.  Every TMEM pipeline
+    configuration (ray threads; R1_TC_CFG = columns per accumulator buffer, buffers per group, ray operand in TMEM)."""
+    cfgs = ((512, None), (512, "64,2,0"), (512, "96,1,1"), (512, "32,3,1"), (384, "128,1,0"), (384, "64,2,0"), (384, "128,1,1"), (384, "64,2,1"),
+            (256, "128,2,0"), (256, "256,1,0"), (256, "96,2,1"), (256, "224,1,1"))
     for name, (w, h, spp) in (("large", (200, 117, 40)), ("medium", (160, 90, 16)), ("small", (64, 36, 8)), ("large", (7, 3, 5))):
-        base, r0 = scenes[name].render(w, h, spp)
-        for threads in (512, 384, 256):
+        base, r0 = scenes[name].render(w, h, spp, variant=r1.VARIANT_MEGAKERNEL_PACKED)
+        monkeypatch.setenv("R1_TC1", "1")                        # r1::megakernel_tc: one MMA-issuing warp per group
+        for threads, cfg in cfgs:
+            if cfg:
+                monkeypatch.setenv("R1_TC_CFG", cfg)
+            else:
+                monkeypatch.delenv("R1_TC_CFG", raising=False)
             alt, ra = scenes[name].render(w, h, spp, variant=r1.VARIANT_MEGAKERNEL_TENSOR, threads=threads)
-            assert np.array_equal(base, alt) and ra.num_rays == r0.num_rays, (name, threads)
+            assert np.array_equal(base, alt) and ra.num_rays == r0.num_rays, (name, threads, cfg)
+    monkeypatch.delenv("R1_TC_CFG", raising=False)
+    monkeypatch.delenv("R1_TC1", raising=False)
+    for groups in (None, "4", "5", "6", "7"):                    # r1::megakernel_tc2 (default): the last ray warp to arrive issues the MMA
+        if groups:
+            monkeypatch.setenv("R1_TC2", groups)
+        for name, (w, h, spp) in (("large", (200, 117, 40)), ("medium", (160, 90, 16)), ("small", (64, 36, 8)), ("large", (7, 3, 5))):
+            base, r0 = scenes[name].render(w, h, spp, variant=r1.VARIANT_MEGAKERNEL_PACKED)
+            alt, ra = scenes[name].render(w, h, spp, variant=r1.VARIANT_MEGAKERNEL_TENSOR)
+            assert np.array_equal(base, alt) and ra.num_rays == r0.num_rays, (name, "tc2", groups)
+    monkeypatch.delenv("R1_TC2", raising=False)
     for world in (2, 3):
         parts = [scenes["large"].render(200, 117, 40, rank=r, world=world, variant=r1.VARIANT_MEGAKERNEL_TENSOR)[0] for r in range(world)]
-        whole, _ = scenes["large"].render(200, 117, 40)
+        whole, _ = scenes["large"].render(200, 117, 40, variant=r1.VARIANT_MEGAKERNEL_PACKED)
         rows = [r1.global_row(lr, r1.DEFAULT_ROW_TILE, r, world) for r in range(world) for lr in range(parts[r].shape[0])]
         assert np.array_equal(np.concatenate(parts)[np.argsort(rows)], whole)
     with pytest.raises(r1.Rays1Error):
         scenes["synth4096"].render(64, 36, 2, variant=r1.VARIANT_MEGAKERNEL_TENSOR)   # above the shared-memory limit of the B tile
+
+
+def test_default_variant_picks_the_kernel_by_scene(r1, scenes, monkeypatch):
+    """R1_VARIANT_MEGAKERNEL: the tensor-core filter for scan-heavy scenes that fit its shared-memory operand, else the packed filter"""
+    name = lambda scene, v=r1.VARIANT_MEGAKERNEL: r1.lib.r1_kernel_name(scenes[scene].handle, v).decode()  # noqa: E731
+    assert name("large") == "megakernel_tc2" and name("medium") == "megakernel_pool" and name("small") == "megakernel_pool"
+    assert name("synth4096") == "megakernel_pool"
+    assert name("large", r1.VARIANT_MEGAKERNEL_PACKED) == "megakernel_pool" and name("large", r1.VARIANT_MEGAKERNEL_TENSOR) == "megakernel_tc2"
+    monkeypatch.setenv("R1_AUTO_TENSOR", "0")
+    assert name("large") == "megakernel_pool"
+    a, ra = scenes["large"].render(96, 54, 8)
+    monkeypatch.delenv("R1_AUTO_TENSOR")
+    b, rb = scenes["large"].render(96, 54, 8)
+    assert np.array_equal(a, b) and ra.num_rays == rb.num_rays
 
 
 def test_hit_empty_and_single(r1, scenes):
@@ -433,7 +465,8 @@ def test_bitwise_invariance(r1, scenes):
     base, r0 = s.render(w, h, spp)
     again, r1_ = s.render(w, h, spp)
     assert np.array_equal(base, again) and r0.num_rays == r1_.num_rays
-    for v in (r1.VARIANT_MEGAKERNEL_SCALAR, r1.VARIANT_MEGAKERNEL_COOP, r1.VARIANT_MEGAKERNEL_DEFERRED, r1.VARIANT_MEGAKERNEL_DUAL):
+    for v in (r1.VARIANT_MEGAKERNEL_SCALAR, r1.VARIANT_MEGAKERNEL_COOP, r1.VARIANT_MEGAKERNEL_DEFERRED, r1.VARIANT_MEGAKERNEL_DUAL,
+              r1.VARIANT_MEGAKERNEL_PACKED, r1.VARIANT_MEGAKERNEL_TENSOR):
         alt, ra = s.render(w, h, spp, variant=v)
         assert np.array_equal(base, alt) and ra.num_rays == r0.num_rays, v
     more, rm = s.render(w, h, spp, blocks_per_sm=2)

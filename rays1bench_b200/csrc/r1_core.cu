@@ -277,10 +277,10 @@ int launch_megakernel_tc_t(int sm_count, const r1::RenderArgs &args, cudaStream_
     return R1_OK;
 }
 
-template <int kGroups, int kChunk>
+template <int kGroups, int kChunk, int kBufs>
 int launch_megakernel_tc2_t(int sm_count, const r1::RenderArgs &args, cudaStream_t stream)
 {
-    auto kern = r1::megakernel_tc2<kGroups, kChunk>;
+    auto kern = r1::megakernel_tc2<kGroups, kChunk, kBufs>;
     const size_t smem = r1::tc2_smem_bytes(kGroups, args.scene.n32);
     if (smem > 227 * 1024) return fail(R1_ERR_LIMIT, "tensor variant: %d ray groups need %zu bytes of shared memory for this scene", kGroups, smem);
     R1_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -297,10 +297,13 @@ int launch_megakernel_tc(int sm_count, const r1::RenderArgs &args, const r1_rend
     if (!args.scene.tcb) return fail(R1_ERR_LIMIT, "the tensor-core filter keeps at most %d spheres in shared memory", r1::tc::kMaxSpheres);
     if (!getenv("R1_TC1")) {   // r1::megakernel_tc2 (default): the last ray warp to arrive issues the MMA; R1_TC2 = ray groups per CTA
         const int groups = getenv("R1_TC2") ? atoi(getenv("R1_TC2")) : (prm.threads > 0 ? prm.threads / 128 : 4);
-        if (groups == 4) return launch_megakernel_tc2_t<4, 128>(sm_count, args, stream);
-        if (groups == 5) return launch_megakernel_tc2_t<5, 96>(sm_count, args, stream);
-        if (groups == 6) return launch_megakernel_tc2_t<6, 64>(sm_count, args, stream);
-        if (groups == 7) return launch_megakernel_tc2_t<7, 64>(sm_count, args, stream);
+        const int bufs = getenv("R1_TC2_BUFS") ? atoi(getenv("R1_TC2_BUFS")) : 1;
+        if (groups == 4 && bufs == 2) return launch_megakernel_tc2_t<4, 64, 2>(sm_count, args, stream);
+        if (groups == 3 && bufs == 2) return launch_megakernel_tc2_t<3, 64, 2>(sm_count, args, stream);
+        if (groups == 4) return launch_megakernel_tc2_t<4, 128, 1>(sm_count, args, stream);
+        if (groups == 5) return launch_megakernel_tc2_t<5, 96, 1>(sm_count, args, stream);
+        if (groups == 6) return launch_megakernel_tc2_t<6, 64, 1>(sm_count, args, stream);
+        if (groups == 7) return launch_megakernel_tc2_t<7, 64, 1>(sm_count, args, stream);
         return fail(R1_ERR_ARG, "the tensor variant runs 4 .. 7 groups of 128 ray threads per CTA (threads = 512 .. 896)");
     }
     // R1_TC1=1: r1::megakernel_tc, one MMA-issuing warp per group (A/B)

@@ -870,12 +870,12 @@ __global__ void __launch_bounds__(kGroups * 160, 1) megakernel_tc(const __grid_c
 // memory (atomicAdd); nobody has to be woken up to issue, no warp spins on behalf of others, and a CTA holds up to 7 groups
 // (896 threads), each with ONE accumulator buffer of kChunk columns.
 struct TcControl2 {
-    uint64_t full[8];                 // per group: accumulator chunk complete (tcgen05.commit; the exit arrival), count 1
+    uint64_t full[8][2];              // per group and buffer: accumulator chunk complete (tcgen05.commit; the exit arrival), count 1
     uint32_t arrived_a[8];            // per group: ray warps with their row written (low byte) / out of work (next byte)
-    uint32_t arrived_e[8];            // per group: ray warps that have read the current chunk
+    uint32_t arrived_e[8][2];         // per group and buffer: ray warps that have read the chunk in it
     uint32_t exit_flag[8];
     uint32_t tmem_base;
-    uint32_t pad_[7];
+    uint32_t pad_[3];
 };
 static_assert(sizeof(TcControl2) % 16 == 0, "TcControl2 is followed by 16-byte aligned tiles");
 
@@ -885,10 +885,11 @@ constexpr size_t tc2_smem_bytes(int groups, int n32)
            (size_t)groups * 4 * sizeof(WarpPool) + 256;          // + alignment slack
 }
 
-template <int kGroups, int kChunk>
+template <int kGroups, int kChunk, int kBufs>
 __global__ void __launch_bounds__(kGroups * 128, 1) megakernel_tc2(const __grid_constant__ RenderArgs a)
 {
-    static_assert(kGroups >= 1 && kGroups <= 8 && kChunk % 32 == 0 && kChunk <= 256 && kGroups * kChunk <= 512, "bad configuration");
+    static_assert(kGroups >= 1 && kGroups <= 8 && kChunk % 32 == 0 && kChunk <= 256 && (kBufs == 1 || kBufs == 2) && kGroups * kChunk * kBufs <= 512,
+                  "bad configuration");
     constexpr int kPieces = kChunk / 32;
     const bool hint = a.tc_flags & 1u;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -913,8 +914,8 @@ __global__ void __launch_bounds__(kGroups * 128, 1) megakernel_tc2(const __grid_
         s_exact[i] = i < a.scene.n_pad ? a.scene.exact[i] : make_float4(0, 0, 0, 0);
     if (threadIdx.x == 0) {
         for (int g = 0; g < 8; ++g) {
-            tc::mbar_init(&ctl.full[g], 1);
-            ctl.arrived_a[g] = 0; ctl.arrived_e[g] = 0; ctl.exit_flag[g] = 0;
+            tc::mbar_init(&ctl.full[g][0], 1); tc::mbar_init(&ctl.full[g][1], 1);
+            ctl.arrived_a[g] = 0; ctl.arrived_e[g][0] = 0; ctl.arrived_e[g][1] = 0; ctl.exit_flag[g] = 0;
         }
         tc::fence_mbar_init();
     }
@@ -932,7 +933,7 @@ __global__ void __launch_bounds__(kGroups * 128, 1) megakernel_tc2(const __grid_
     WarpPool &pool = pools[threadIdx.x >> 5];
     unsigned char *a_tile = s_a + (size_t)g * 128 * tc::kRowBytes;
     const uint32_t a_smem = tc::smem_u32(a_tile), b_smem = tc::smem_u32(s_b);
-    const uint32_t d_tmem = tmem_base + (uint32_t)(g * kChunk), t_lane = d_tmem + ((uint32_t)(w * 32) << 16);
+    const uint32_t d_tmem = tmem_base + (uint32_t)(g * kChunk * kBufs), t_lane = d_tmem + ((uint32_t)(w * 32) << 16);
     bool active = false, exhausted = false;
     PoolState ps;
     ps.dry = false; ps.ready = 0; ps.w_next = 0; ps.w_end = 0;
@@ -963,11 +964,16 @@ __global__ void __launch_bounds__(kGroups * 128, 1) megakernel_tc2(const __grid_
                 if ((tot >> 8) == 4u) {
                     *reinterpret_cast<volatile uint32_t *>(&ctl.exit_flag[g]) = 1u;
                     __threadfence_block();
-                    tc::mbar_arrive(&ctl.full[g]);
+                    tc::mbar_arrive(&ctl.full[g][it % kBufs]);
                 } else {
                     tc::tc_fence_after();
-                    tc::mma_chunk(d_tmem, a_smem, b_smem, min(kChunk, n32), tc::kLBO, tc::kSBO);
-                    tc::mma_commit(&ctl.full[g]);
+#pragma unroll
+                    for (int j = 0; j < kBufs; ++j)
+                        if (j < nchunks) {                       // the first kBufs chunks: every buffer is free at the start of a scan
+                            const uint32_t b = (it + j) % kBufs;
+                            tc::mma_chunk(d_tmem + b * kChunk, a_smem, b_smem + (uint32_t)j * (kChunk / 8) * tc::kSBO, min(kChunk, n32 - j * kChunk), tc::kLBO, tc::kSBO);
+                            tc::mma_commit(&ctl.full[g][b]);
+                        }
                 }
             }
         }
@@ -977,7 +983,8 @@ __global__ void __launch_bounds__(kGroups * 128, 1) megakernel_tc2(const __grid_
         int hit = -1;
         bool leave = false;
         for (int c = 0; c < nchunks; ++c, ++it) {
-            tc::mbar_wait(&ctl.full[g], it & 1u, hint);
+            const uint32_t b = it % kBufs, t_buf = t_lane + b * kChunk;
+            tc::mbar_wait(&ctl.full[g][b], (it / kBufs) & 1u, hint);
             if (c == 0 && *reinterpret_cast<volatile uint32_t *>(&ctl.exit_flag[g])) { leave = true; break; }
             tc::tc_fence_after();
             const int pieces = min(kPieces, (n32 - c * kChunk) >> 5);   // warp-uniform: the last chunk may be short
@@ -987,35 +994,36 @@ __global__ void __launch_bounds__(kGroups * 128, 1) megakernel_tc2(const __grid_
                 cand[h] = 0; cand[h + 1] = 0;
                 if (kGroups <= 5 && h + 1 < pieces) {           // (6 and 7 groups have 72 .. 80 registers: one load at a time)
                     uint32_t v0[32], v1[32];
-                    tc::tmem_ld32_issue(t_lane + 32 * h, v0);
-                    tc::tmem_ld32_issue(t_lane + 32 * h + 32, v1);
+                    tc::tmem_ld32_issue(t_buf + 32 * h, v0);
+                    tc::tmem_ld32_issue(t_buf + 32 * h + 32, v1);
                     tc::tmem_wait(v0, v1);
                     cand[h] = tc::flagged(v0);
                     cand[h + 1] = tc::flagged(v1);
                 } else {
                     if (h < pieces) {
                         uint32_t v[32];
-                        tc::tmem_ld32(t_lane + 32 * h, v);
+                        tc::tmem_ld32(t_buf + 32 * h, v);
                         cand[h] = tc::flagged(v);
                     }
                     if (h + 1 < pieces) {
                         uint32_t v[32];
-                        tc::tmem_ld32(t_lane + 32 * h + 32, v);
+                        tc::tmem_ld32(t_buf + 32 * h + 32, v);
                         cand[h + 1] = tc::flagged(v);
                     }
                 }
             }
-            if (c + 1 < nchunks) {                               // warp-uniform
+            if (c + kBufs < nchunks) {                           // warp-uniform: this buffer is needed again in this scan
                 tc::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
                     __threadfence_block();
-                    if (atomicAdd(&ctl.arrived_e[g], 1u) == 3u) {    // last reader: the buffer is free, issue the next chunk
-                        *reinterpret_cast<volatile uint32_t *>(&ctl.arrived_e[g]) = 0u;
+                    if (atomicAdd(&ctl.arrived_e[g][b], 1u) == 3u) {  // last reader: the buffer is free, issue the chunk that reuses it
+                        *reinterpret_cast<volatile uint32_t *>(&ctl.arrived_e[g][b]) = 0u;
                         __threadfence_block();
                         tc::tc_fence_after();
-                        tc::mma_chunk(d_tmem, a_smem, b_smem + (uint32_t)(c + 1) * (kChunk / 8) * tc::kSBO, min(kChunk, n32 - (c + 1) * kChunk), tc::kLBO, tc::kSBO);
-                        tc::mma_commit(&ctl.full[g]);
+                        tc::mma_chunk(d_tmem + b * kChunk, a_smem, b_smem + (uint32_t)(c + kBufs) * (kChunk / 8) * tc::kSBO, min(kChunk, n32 - (c + kBufs) * kChunk),
+                                      tc::kLBO, tc::kSBO);
+                        tc::mma_commit(&ctl.full[g][b]);
                     }
                 }
                 __syncwarp();

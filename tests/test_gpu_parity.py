@@ -192,14 +192,17 @@ def test_tensor_variant_renders_the_same_bytes(r1, scenes, monkeypatch):
             assert np.array_equal(base, alt) and ra.num_rays == r0.num_rays, (name, threads, cfg)
     monkeypatch.delenv("R1_TC_CFG", raising=False)
     monkeypatch.delenv("R1_TC1", raising=False)
-    for groups in (None, "4", "5", "6", "7"):                    # r1::megakernel_tc2 (default): the last ray warp to arrive issues the MMA
+    for groups, bufs in ((None, "1"), ("4", "1"), ("5", "1"), ("6", "1"), ("7", "1"), ("4", "2"), ("3", "2")):
+        # r1::megakernel_tc2 (default): the last ray warp to arrive issues the MMA; ray groups per CTA, accumulator buffers per group
+        monkeypatch.setenv("R1_TC2_BUFS", bufs)
         if groups:
             monkeypatch.setenv("R1_TC2", groups)
         for name, (w, h, spp) in (("large", (200, 117, 40)), ("medium", (160, 90, 16)), ("small", (64, 36, 8)), ("large", (7, 3, 5))):
             base, r0 = scenes[name].render(w, h, spp, variant=r1.VARIANT_MEGAKERNEL_PACKED)
             alt, ra = scenes[name].render(w, h, spp, variant=r1.VARIANT_MEGAKERNEL_TENSOR)
-            assert np.array_equal(base, alt) and ra.num_rays == r0.num_rays, (name, "tc2", groups)
+            assert np.array_equal(base, alt) and ra.num_rays == r0.num_rays, (name, "tc2", groups, bufs)
     monkeypatch.delenv("R1_TC2", raising=False)
+    monkeypatch.delenv("R1_TC2_BUFS", raising=False)
     for world in (2, 3):
         parts = [scenes["large"].render(200, 117, 40, rank=r, world=world, variant=r1.VARIANT_MEGAKERNEL_TENSOR)[0] for r in range(world)]
         whole, _ = scenes["large"].render(200, 117, 40, variant=r1.VARIANT_MEGAKERNEL_PACKED)

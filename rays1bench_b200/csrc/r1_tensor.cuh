@@ -11,7 +11,7 @@
 // the K dimension:  K = 11 + 11 + 10 = 32 (the constant sphere feature has no low part) = four K = 8 instructions.
 // Per test the CUDA cores are left with ONE instruction (the sign bit of e into the candidate mask) instead of eight packed FMA.
 // The split products carry 2^-21 relative error and the accumulation order inside the tensor core is not documented, so the
-// margins are wider than the FP32 filter's (kMargin below, against 2^-17); the measured error is in DESIGN.md section 4.4 and
+// margins are wider than the FP32 filter's (kMargin below, against 2^-17); the measured error is in DESIGN.md section 4.0 and
 // tests/test_gpu_parity.py::test_tensor_filter_is_conservative checks the filter against the exact test on the GPU.
 #pragma once
 #include <cstdint>

@@ -143,7 +143,7 @@ int r1_deinterleave_rows(int device, const void *d_gathered, uint64_t stride, vo
 /* Hitable::hit (rayweek1.cpp:152-339); index = -1 on a miss.  dir must be unit length (Ray ctor, :104-108). */
 int r1_trace_rays(r1_scene *scene, int n, const float *org, const float *dir, float t_min, float t_max, int variant,
                   int32_t *index, float *t, float *p, float *normal);
-/* Name of the trace kernel `variant` resolves to for this scene with default tuning ("megakernel_tc2", "megakernel_pool", ...);
+/* Name of the trace kernel `variant` resolves to for this scene with default tuning ("megakernel_tc3", "megakernel_pool", ...);
  * static storage. */
 const char *r1_kernel_name(r1_scene *scene, int variant);
 /* Values of the tensor-core FILTER (R1_VARIANT_MEGAKERNEL_TENSOR) for n rays against every sphere: e[ray * n32 + sphere], n32 =

@@ -292,11 +292,36 @@ int launch_megakernel_tc2_t(int sm_count, const r1::RenderArgs &args, cudaStream
     return R1_OK;
 }
 
+template <int kGroups>
+int launch_megakernel_tc3_t(int sm_count, const r1::RenderArgs &args, cudaStream_t stream)
+{
+    auto kern = r1::megakernel_tc3<kGroups>;
+    const size_t smem = r1::tc2_smem_bytes(kGroups, args.scene.n32);
+    if (smem > 227 * 1024) return fail(R1_ERR_LIMIT, "tensor variant: %d ray groups need %zu bytes of shared memory for this scene", kGroups, smem);
+    R1_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = sm_count;
+    const unsigned long long max_ctas = (args.n_samples + kGroups * 128 - 1) / (kGroups * 128);
+    if ((unsigned long long)grid > max_ctas) grid = (int)std::max<unsigned long long>(1, max_ctas);
+    kern<<<grid, kGroups * 128, smem, stream>>>(args);
+    R1_CUDA(cudaGetLastError());
+    return R1_OK;
+}
+
 int launch_megakernel_tc(int sm_count, const r1::RenderArgs &args, const r1_render_params &prm, cudaStream_t stream)
 {
     if (!args.scene.tcb) return fail(R1_ERR_LIMIT, "the tensor-core filter keeps at most %d spheres in shared memory", r1::tc::kMaxSpheres);
-    if (!getenv("R1_TC1")) {   // r1::megakernel_tc2 (default): the last ray warp to arrive issues the MMA; R1_TC2 = ray groups per CTA
-        const int groups = getenv("R1_TC2") ? atoi(getenv("R1_TC2")) : (prm.threads > 0 ? prm.threads / 128 : 4);
+    if (!getenv("R1_TC1") && !getenv("R1_TC2")) {
+        // r1::megakernel_tc3 (default): the last ray warp to arrive issues the MMA, accumulator buffers pooled among the groups;
+        // R1_TC3 (or threads / 128) = ray groups per CTA.  Measured on the large scene: 4 groups 9.70, 5: 10.34, 6: 9.92, 7: 9.69 G rays/s
+        const int groups = getenv("R1_TC3") ? atoi(getenv("R1_TC3")) : (prm.threads > 0 ? prm.threads / 128 : 5);
+        if (groups == 4) return launch_megakernel_tc3_t<4>(sm_count, args, stream);
+        if (groups == 5) return launch_megakernel_tc3_t<5>(sm_count, args, stream);
+        if (groups == 6) return launch_megakernel_tc3_t<6>(sm_count, args, stream);
+        if (groups == 7) return launch_megakernel_tc3_t<7>(sm_count, args, stream);
+        return fail(R1_ERR_ARG, "the tensor variant runs 4 .. 7 groups of 128 ray threads per CTA (threads = 512 .. 896)");
+    }
+    if (!getenv("R1_TC1")) {   // R1_TC2 = groups (A/B): r1::megakernel_tc2, one accumulator buffer (or two: R1_TC2_BUFS=2) owned by each group
+        const int groups = atoi(getenv("R1_TC2"));
         const int bufs = getenv("R1_TC2_BUFS") ? atoi(getenv("R1_TC2_BUFS")) : 1;
         if (groups == 4 && bufs == 2) return launch_megakernel_tc2_t<4, 64, 2>(sm_count, args, stream);
         if (groups == 3 && bufs == 2) return launch_megakernel_tc2_t<3, 64, 2>(sm_count, args, stream);
@@ -304,7 +329,7 @@ int launch_megakernel_tc(int sm_count, const r1::RenderArgs &args, const r1_rend
         if (groups == 5) return launch_megakernel_tc2_t<5, 96, 1>(sm_count, args, stream);
         if (groups == 6) return launch_megakernel_tc2_t<6, 64, 1>(sm_count, args, stream);
         if (groups == 7) return launch_megakernel_tc2_t<7, 64, 1>(sm_count, args, stream);
-        return fail(R1_ERR_ARG, "the tensor variant runs 4 .. 7 groups of 128 ray threads per CTA (threads = 512 .. 896)");
+        return fail(R1_ERR_ARG, "R1_TC2 must be 3 .. 7");
     }
     // R1_TC1=1: r1::megakernel_tc, one MMA-issuing warp per group (A/B)
     const int threads = prm.threads > 0 ? prm.threads : (getenv("R1_TC_THREADS") ? atoi(getenv("R1_TC_THREADS")) : 512);
@@ -848,7 +873,7 @@ const char *r1_kernel_name(r1_scene *scene, int variant)
     prm.variant = variant;
     switch (resolve_variant(cp->dev, prm)) {
     case R1_VARIANT_WAVEFRONT: return "wf_intersect + wf_shade (graph loop)";
-    case R1_VARIANT_MEGAKERNEL_TENSOR: return getenv("R1_TC1") ? "megakernel_tc" : "megakernel_tc2";
+    case R1_VARIANT_MEGAKERNEL_TENSOR: return getenv("R1_TC1") ? "megakernel_tc" : (getenv("R1_TC2") ? "megakernel_tc2" : "megakernel_tc3");
     case R1_VARIANT_MEGAKERNEL_DUAL: return "megakernel_pool2";
     default: return (getenv("R1_POOL") && atoi(getenv("R1_POOL")) == 0) ? "megakernel" : "megakernel_pool";
     }

@@ -881,7 +881,7 @@ static_assert(sizeof(TcControl2) % 16 == 0, "TcControl2 is followed by 16-byte a
 
 constexpr size_t tc2_smem_bytes(int groups, int n32)
 {
-    return (size_t)kSmemSpheres + sizeof(TcControl2) + (size_t)n32 * tc::kRowBytes + (size_t)n32 * 16 + (size_t)groups * 128 * tc::kRowBytes +
+    return (size_t)kSmemSpheres + 256 + (size_t)n32 * tc::kRowBytes + (size_t)n32 * 16 + (size_t)groups * 128 * tc::kRowBytes +
            (size_t)groups * 4 * sizeof(WarpPool) + 256;          // + alignment slack
 }
 
@@ -1028,6 +1028,205 @@ __global__ void __launch_bounds__(kGroups * 128, 1) megakernel_tc2(const __grid_
                 }
                 __syncwarp();
             }
+#pragma unroll
+            for (int h = 0; h < kPieces; ++h)
+                if (cand[h]) exact_candidates(cand[h], s_exact, c * kChunk + 32 * h, o, d, kTMin, t, hit);
+        }
+        if (leave) break;
+
+        if (active) {
+            ++nrays;
+            f3 contrib;
+            const float4 e = hit >= 0 ? s_exact[hit] : make_float4(0, 0, 0, 0);
+            if (shade_step(a, hit, t, e, tab, o, d, thr, depth, rng, contrib)) {
+                accumulate_sample(a, lp, contrib);
+                active = false;
+            }
+        }
+    }
+    unsigned long long total = nrays;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(kFull, total, off);
+    if (lane == 0 && total) atomicAdd(a.num_rays, total);
+    tc::tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tc::tmem_dealloc(tmem_base, 512);
+}
+
+// megakernel_tc2 with the accumulator buffers POOLED: a group holds one of the four 128-column TMEM buffers only while it scans
+// (first MMA issued ... last chunk read) and hands it back for the exact tests of the last chunk, shading, the pop and the row
+// build, so a CTA carries more ray groups (5 .. 7) than TMEM has buffers.  free_mask: bit b = buffer b is free; the last warp to
+// write its row takes a buffer (atomicAnd), the last reader of the last chunk returns it (atomicOr).
+struct TcControl3 {
+    uint64_t full[8];                 // per group: accumulator chunk complete (tcgen05.commit; the exit arrival), count 1
+    uint32_t arrived_a[8];            // per group: ray warps with their row written (low byte) / out of work (next byte)
+    uint32_t arrived_e[8];            // per group: ray warps that have read the current chunk
+    uint32_t exit_flag[8];
+    uint32_t buf_of[8];               // per group: the buffer its current scan holds
+    uint32_t free_mask;
+    uint32_t tmem_base;
+    uint32_t pad_[2];
+};
+static_assert(sizeof(TcControl3) % 16 == 0, "TcControl3 is followed by 16-byte aligned tiles");
+
+template <int kGroups>
+__global__ void __launch_bounds__(kGroups * 128, 1) megakernel_tc3(const __grid_constant__ RenderArgs a)
+{
+    constexpr int kChunk = 128, kPool = 4;
+    static_assert(kGroups >= 4 && kGroups <= 7, "bad configuration");
+    constexpr int kPieces = kChunk / 32;
+    const bool hint = a.tc_flags & 1u;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint16_t *s_tab = reinterpret_cast<uint16_t *>(smem_raw + 16);
+    unsigned char *p = smem_raw + ((kSmemSpheres + 127) & ~127);
+    TcControl3 &ctl = *reinterpret_cast<TcControl3 *>(p);
+    p += (sizeof(TcControl3) + 127) & ~127;
+    unsigned char *s_b = p;
+    const int n32 = a.scene.n32;
+    p += (size_t)n32 * tc::kRowBytes;
+    float4 *s_exact = reinterpret_cast<float4 *>(p);
+    p += (size_t)n32 * 16;
+    unsigned char *s_a = p;
+    p += (size_t)kGroups * 128 * tc::kRowBytes;
+    WarpPool *pools = reinterpret_cast<WarpPool *>(p);
+
+    for (int i = threadIdx.x; i < R1_RSQRT12_ENTRIES / 2; i += blockDim.x)
+        reinterpret_cast<uint32_t *>(s_tab)[i] = reinterpret_cast<const uint32_t *>(g_rsqrt12)[i];
+    for (int i = threadIdx.x; i < n32 * (tc::kRowBytes / 16); i += blockDim.x)
+        reinterpret_cast<uint4 *>(s_b)[i] = reinterpret_cast<const uint4 *>(a.scene.tcb)[i];
+    for (int i = threadIdx.x; i < n32; i += blockDim.x)
+        s_exact[i] = i < a.scene.n_pad ? a.scene.exact[i] : make_float4(0, 0, 0, 0);
+    if (threadIdx.x == 0) {
+        for (int g = 0; g < 8; ++g) {
+            tc::mbar_init(&ctl.full[g], 1);
+            ctl.arrived_a[g] = 0; ctl.arrived_e[g] = 0; ctl.exit_flag[g] = 0; ctl.buf_of[g] = 0;
+        }
+        ctl.free_mask = (1u << kPool) - 1u;
+        tc::fence_mbar_init();
+    }
+    tc::fence_proxy_async();                                     // the B tile is read by the tensor core (async proxy)
+    if (threadIdx.x < 32) tc::tmem_alloc(&ctl.tmem_base, 512);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(&ctl.tmem_base);
+    const int nchunks = (n32 + kChunk - 1) / kChunk;
+    const unsigned lane = threadIdx.x & 31u;
+    const int g = threadIdx.x >> 7, w = (threadIdx.x >> 5) & 3, r = threadIdx.x & 127;
+    const uint16_t *tab = s_tab;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    WarpPool &pool = pools[threadIdx.x >> 5];
+    unsigned char *a_tile = s_a + (size_t)g * 128 * tc::kRowBytes;
+    const uint32_t a_smem = tc::smem_u32(a_tile), b_smem = tc::smem_u32(s_b);
+    const uint32_t t_lane = tmem_base + ((uint32_t)(w * 32) << 16);
+    bool active = false, exhausted = false;
+    PoolState ps;
+    ps.dry = false; ps.ready = 0; ps.w_next = 0; ps.w_end = 0;
+    const uint32_t lanes_x = gridDim.x * blockDim.x * a.sched_div;
+    uint32_t lp = 0, it = 0, nrays = 0;
+    int depth = 0;
+    f3 thr = mk3(1, 1, 1), o = mk3(0, 0, 0), d = mk3(0, 0, 0);
+    Rng rng;
+    rng.k0 = 0; rng.k1 = 0;
+
+    for (;;) {
+        const bool want = !active && !exhausted;
+        const unsigned need = __ballot_sync(kFull, want);
+        if (need) pool_take(a, pool, ps, tab, lane, lt_mask, lanes_x, need, want, active, exhausted, o, d, lp, rng, thr, depth);
+        const bool warp_done = __all_sync(kFull, exhausted);
+
+        tc::write_ray_row(a_tile, r, o, d, active);
+        tc::fence_proxy_async();
+        tc::tc_fence_before();                                   // this warp's reads of the previous scan's last chunk are complete
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t mine = 1u + (warp_done ? 0x100u : 0u);
+            __threadfence_block();
+            const uint32_t tot = atomicAdd(&ctl.arrived_a[g], mine) + mine;
+            if ((tot & 0xffu) == 4u) {                           // last of the group: start the scan (or end the group)
+                *reinterpret_cast<volatile uint32_t *>(&ctl.arrived_a[g]) = 0u;
+                __threadfence_block();
+                if ((tot >> 8) == 4u) {
+                    *reinterpret_cast<volatile uint32_t *>(&ctl.exit_flag[g]) = 1u;
+                    __threadfence_block();
+                    tc::mbar_arrive(&ctl.full[g]);
+                } else {
+                    uint32_t b = 0, spins = 0;
+                    for (;;) {                                   // take a free accumulator buffer
+                        const uint32_t m = *reinterpret_cast<volatile uint32_t *>(&ctl.free_mask);
+                        if (m) {
+                            b = (uint32_t)__ffs((int)m) - 1u;
+                            if (atomicAnd(&ctl.free_mask, ~(1u << b)) & (1u << b)) break;
+                        } else {
+                            __nanosleep(64);
+                            if (++spins > (1u << 24)) __trap();
+                        }
+                    }
+                    __threadfence_block();
+                    *reinterpret_cast<volatile uint32_t *>(&ctl.buf_of[g]) = b;
+                    tc::tc_fence_after();
+                    tc::mma_chunk(tmem_base + b * kChunk, a_smem, b_smem, min(kChunk, n32), tc::kLBO, tc::kSBO);
+                    tc::mma_commit(&ctl.full[g]);
+                }
+            }
+        }
+        __syncwarp();
+
+        float t = kTMax;
+        int hit = -1;
+        bool leave = false;
+        uint32_t b = 0;
+        for (int c = 0; c < nchunks; ++c, ++it) {
+            tc::mbar_wait(&ctl.full[g], it & 1u, hint);
+            if (c == 0) {
+                if (*reinterpret_cast<volatile uint32_t *>(&ctl.exit_flag[g])) { leave = true; break; }
+                b = *reinterpret_cast<volatile uint32_t *>(&ctl.buf_of[g]);
+            }
+            const uint32_t t_buf = t_lane + b * kChunk;
+            tc::tc_fence_after();
+            const int pieces = min(kPieces, (n32 - c * kChunk) >> 5);   // warp-uniform: the last chunk may be short
+            uint32_t cand[kPieces + 1];
+#pragma unroll
+            for (int h = 0; h < kPieces; h += 2) {               // two loads in flight, eight independent sign-gather chains
+                cand[h] = 0; cand[h + 1] = 0;
+                if (kGroups <= 5 && h + 1 < pieces) {           // (6 and 7 groups have 72 .. 80 registers: one load at a time)
+                    uint32_t v0[32], v1[32];
+                    tc::tmem_ld32_issue(t_buf + 32 * h, v0);
+                    tc::tmem_ld32_issue(t_buf + 32 * h + 32, v1);
+                    tc::tmem_wait(v0, v1);
+                    cand[h] = tc::flagged(v0);
+                    cand[h + 1] = tc::flagged(v1);
+                } else {
+                    if (h < pieces) {
+                        uint32_t v[32];
+                        tc::tmem_ld32(t_buf + 32 * h, v);
+                        cand[h] = tc::flagged(v);
+                    }
+                    if (h + 1 < pieces) {
+                        uint32_t v[32];
+                        tc::tmem_ld32(t_buf + 32 * h + 32, v);
+                        cand[h + 1] = tc::flagged(v);
+                    }
+                }
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                if (atomicAdd(&ctl.arrived_e[g], 1u) == 3u) {        // last reader
+                    *reinterpret_cast<volatile uint32_t *>(&ctl.arrived_e[g]) = 0u;
+                    __threadfence_block();
+                    if (c + 1 < nchunks) {                           // the buffer is free for the next chunk of this scan
+                        tc::tc_fence_after();
+                        tc::mma_chunk(tmem_base + b * kChunk, a_smem, b_smem + (uint32_t)(c + 1) * (kChunk / 8) * tc::kSBO, min(kChunk, n32 - (c + 1) * kChunk),
+                                      tc::kLBO, tc::kSBO);
+                        tc::mma_commit(&ctl.full[g]);
+                    } else {
+                        atomicOr(&ctl.free_mask, 1u << b);           // scan over: hand the buffer back
+                    }
+                }
+            }
+            __syncwarp();
 #pragma unroll
             for (int h = 0; h < kPieces; ++h)
                 if (cand[h]) exact_candidates(cand[h], s_exact, c * kChunk + 32 * h, o, d, kTMin, t, hit);

@@ -192,17 +192,24 @@ def test_tensor_variant_renders_the_same_bytes(r1, scenes, monkeypatch):
             assert np.array_equal(base, alt) and ra.num_rays == r0.num_rays, (name, threads, cfg)
     monkeypatch.delenv("R1_TC_CFG", raising=False)
     monkeypatch.delenv("R1_TC1", raising=False)
-    for groups, bufs in ((None, "1"), ("4", "1"), ("5", "1"), ("6", "1"), ("7", "1"), ("4", "2"), ("3", "2")):
-        # r1::megakernel_tc2 (default): the last ray warp to arrive issues the MMA; ray groups per CTA, accumulator buffers per group
+    for groups, bufs in (("4", "1"), ("5", "1"), ("6", "1"), ("7", "1"), ("4", "2"), ("3", "2")):
+        # r1::megakernel_tc2: the last ray warp to arrive issues the MMA; ray groups per CTA, accumulator buffers owned by each group
         monkeypatch.setenv("R1_TC2_BUFS", bufs)
-        if groups:
-            monkeypatch.setenv("R1_TC2", groups)
+        monkeypatch.setenv("R1_TC2", groups)
         for name, (w, h, spp) in (("large", (200, 117, 40)), ("medium", (160, 90, 16)), ("small", (64, 36, 8)), ("large", (7, 3, 5))):
             base, r0 = scenes[name].render(w, h, spp, variant=r1.VARIANT_MEGAKERNEL_PACKED)
             alt, ra = scenes[name].render(w, h, spp, variant=r1.VARIANT_MEGAKERNEL_TENSOR)
             assert np.array_equal(base, alt) and ra.num_rays == r0.num_rays, (name, "tc2", groups, bufs)
     monkeypatch.delenv("R1_TC2", raising=False)
     monkeypatch.delenv("R1_TC2_BUFS", raising=False)
+    for groups in (None, "4", "5", "6", "7"):                    # r1::megakernel_tc3 (default): accumulator buffers pooled among the groups
+        if groups:
+            monkeypatch.setenv("R1_TC3", groups)
+        for name, (w, h, spp) in (("large", (200, 117, 40)), ("medium", (160, 90, 16)), ("small", (64, 36, 8)), ("large", (7, 3, 5))):
+            base, r0 = scenes[name].render(w, h, spp, variant=r1.VARIANT_MEGAKERNEL_PACKED)
+            alt, ra = scenes[name].render(w, h, spp, variant=r1.VARIANT_MEGAKERNEL_TENSOR)
+            assert np.array_equal(base, alt) and ra.num_rays == r0.num_rays, (name, "tc3", groups)
+    monkeypatch.delenv("R1_TC3", raising=False)
     for world in (2, 3):
         parts = [scenes["large"].render(200, 117, 40, rank=r, world=world, variant=r1.VARIANT_MEGAKERNEL_TENSOR)[0] for r in range(world)]
         whole, _ = scenes["large"].render(200, 117, 40, variant=r1.VARIANT_MEGAKERNEL_PACKED)
@@ -215,9 +222,9 @@ def test_tensor_variant_renders_the_same_bytes(r1, scenes, monkeypatch):
 def test_default_variant_picks_the_kernel_by_scene(r1, scenes, monkeypatch):
     """R1_VARIANT_MEGAKERNEL: the tensor-core filter for scan-heavy scenes that fit its shared-memory operand, else the packed filter"""
     name = lambda scene, v=r1.VARIANT_MEGAKERNEL: r1.lib.r1_kernel_name(scenes[scene].handle, v).decode()  # noqa: E731
-    assert name("large") == "megakernel_tc2" and name("medium") == "megakernel_pool" and name("small") == "megakernel_pool"
+    assert name("large") == "megakernel_tc3" and name("medium") == "megakernel_pool" and name("small") == "megakernel_pool"
     assert name("synth4096") == "megakernel_pool"
-    assert name("large", r1.VARIANT_MEGAKERNEL_PACKED) == "megakernel_pool" and name("large", r1.VARIANT_MEGAKERNEL_TENSOR) == "megakernel_tc2"
+    assert name("large", r1.VARIANT_MEGAKERNEL_PACKED) == "megakernel_pool" and name("large", r1.VARIANT_MEGAKERNEL_TENSOR) == "megakernel_tc3"
     monkeypatch.setenv("R1_AUTO_TENSOR", "0")
     assert name("large") == "megakernel_pool"
     a, ra = scenes["large"].render(96, 54, 8)

@@ -362,7 +362,7 @@ int launch_megakernel(int sm_count, const r1::RenderArgs &args, const r1_render_
 }
 
 // R1_VARIANT_MEGAKERNEL = the fastest megakernel for the scene.  Measured on B200: the tensor-core filter wins on the large scene
-// (485 spheres: 10.2 against 6.2 G rays/s) and loses where a scan is short (medium, 58 spheres: 25 against 34 G).  Explicit
+// (485 spheres: 10.3 against 6.2 G rays/s) and loses where a scan is short (medium, 58 spheres: 25 against 34 G).  Explicit
 // tuning knobs (blocks_per_sm, threads, R1_POOL=0) address the packed kernel; R1_AUTO_TENSOR=0 keeps it everywhere.
 int resolve_variant(const r1::DevScene &dev, const r1_render_params &prm)
 {

@@ -598,6 +598,9 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel_pool2(const
 
 // ------------------------------------------------------------------------------------------------ megakernel, tensor-core filter
 // R1_VARIANT_MEGAKERNEL_TENSOR: the path state machine of megakernel_pool with the filter on the tensor cores (r1_tensor.cuh).
+// Three generations, all kept for A/B: megakernel_tc below (R1_TC1=1: one MMA-issuing warp per group),
+// megakernel_tc2 (R1_TC2=groups: the last ray warp to arrive issues, every group owns its accumulator buffer) and megakernel_tc3
+// (default: the four accumulator buffers are pooled among five groups).
 //
 // CTA = kGroups ray groups of 128 threads (4 warps, warp w of a group owns TMEM lanes 32 w .. 32 w + 31, one ray per lane) +
 // one MMA-issuing warp per group.  Per scan every thread writes its ray's lifted TF32 row into the group's A tile; the issuing
@@ -605,7 +608,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) megakernel_pool2(const
 // K = 8) per chunk into one of the group's two 64-column accumulator buffers, tcgen05.commit onto the buffer's `full` mbarrier.
 // The ray warps wait for `full`, read their 64 filter values with two tcgen05.ld, release the buffer (`empty`, one arrival per
 // warp) and resolve the flagged spheres with the same exact test as every other variant -- same hits, same bytes out.
-// TMEM: kGroups x 2 buffers x 64 columns = all 512 columns at kGroups = 4.
+// TMEM columns of a group: kBufs accumulator buffers of kChunk columns (+ 32 for the ray operand if kATmem).
 struct TcControl {
     uint64_t a_full[4];               // per group: the four ray warps have written their rows (count 4)
     uint64_t full[4][4];              // per group and buffer: accumulator chunk complete (tcgen05.commit, count 1)

@@ -146,6 +146,11 @@ int r1_trace_rays(r1_scene *scene, int n, const float *org, const float *dir, fl
 /* Name of the trace kernel `variant` resolves to for this scene with default tuning ("megakernel_tc3", "megakernel_pool", ...);
  * static storage. */
 const char *r1_kernel_name(r1_scene *scene, int variant);
+/* Host only (no device needed): the sphere operand of the tensor-core filter for this scene -- n32 rows (sphere count padded to
+ * 32) of 128 bytes: 32 TF32 words {hi x 11 | hi x 11 | lo x 10} of the 11 lifted features in the tcgen05 K-major no-swizzle
+ * layout, byte offset of (row r, word k) = (r / 8) * 1024 + (k / 4) * 128 + (r % 8) * 16 + (k % 4) * 4.  out = NULL: only
+ * *n32_out is set.  R1_ERR_LIMIT for empty scenes and above 768 spheres. */
+int r1_tensor_operand(const r1_scene *scene, void *out, uint64_t out_bytes, uint32_t *n32_out);
 /* Values of the tensor-core FILTER (R1_VARIANT_MEGAKERNEL_TENSOR) for n rays against every sphere: e[ray * n32 + sphere], n32 =
  * sphere count padded to 32; the filter flags a sphere iff the sign bit of e is clear, and must flag every sphere Hitable::hit's
  * discriminant test (rayweek1.cpp:192-204) accepts.  layout = 0. */

@@ -78,6 +78,7 @@ def _load():
         "r1_deinterleave_rows": (ci, [ci, vp, C.c_uint64, vp, ci, ci, ci, ci, vp]),
         "r1_trace_rays": (ci, [vp, ci, f32p, f32p, cf, cf, ci, i32p, f32p, f32p, f32p]),
         "r1_filter_probe": (ci, [vp, ci, f32p, f32p, ci, f32p]),
+        "r1_tensor_operand": (ci, [vp, u8p, C.c_uint64, C.POINTER(C.c_uint32)]),
         "r1_scatter": (ci, [vp, ci, f32p, f32p, f32p, i32p, f32p, f32p, i32p, f32p, f32p]),
         "r1_get_ray": (ci, [vp, ci, f32p, f32p, f32p, f32p, f32p]),
         "r1_replay_pixels": (ci, [vp, ci, i32p, ci, ci, ci, ci, u32p, u32p, f32p, u32p]),
@@ -204,6 +205,17 @@ class Scene:
         nrm = np.zeros((n, 3), np.float32)
         _check(lib.r1_trace_rays(self.handle, n, org, dir_, t_min, t_max, variant, idx, t, p, nrm), "r1_trace_rays")
         return idx, t, p, nrm
+
+    def tensor_operand(self):
+        """r1_tensor_operand (host only): the sphere operand of the tensor-core filter as float32 [n32, 32] = {hi | hi | lo} words
+        of the 11 lifted features, un-tiled from the tcgen05 core-matrix layout."""
+        n32 = C.c_uint32(0)
+        n = (self.count() + 31) // 32 * 32
+        raw = np.zeros(max(n, 32) * 128, np.uint8)
+        _check(lib.r1_tensor_operand(self.handle, raw, raw.size, C.byref(n32)), "r1_tensor_operand")
+        r, k = np.meshgrid(np.arange(n32.value), np.arange(32), indexing="ij")
+        off = (r // 8) * 1024 + (k // 4) * 128 + (r % 8) * 16 + (k % 4) * 4
+        return raw.view(np.float32)[off // 4]
 
     def filter_probe(self, org, dir_, n_spheres, layout=0):
         """r1_filter_probe: values of the tensor-core filter, shape (rays, n32); sign bit clear = sphere flagged."""

@@ -309,7 +309,7 @@ int launch_megakernel_tc3_t(int sm_count, const r1::RenderArgs &args, cudaStream
 
 int launch_megakernel_tc(int sm_count, const r1::RenderArgs &args, const r1_render_params &prm, cudaStream_t stream)
 {
-    if (!args.scene.tcb) return fail(R1_ERR_LIMIT, "the tensor-core filter keeps at most %d spheres in shared memory", r1::tc::kMaxSpheres);
+    if (!args.scene.tcb) return fail(R1_ERR_LIMIT, "the tensor-core filter takes scenes of 1 .. %d spheres (its operand lives in shared memory)", r1::tc::kMaxSpheres);
     if (!getenv("R1_TC1") && !getenv("R1_TC2")) {
         // r1::megakernel_tc3 (default): the last ray warp to arrive issues the MMA, accumulator buffers pooled among the groups;
         // R1_TC3 (or threads / 128) = ray groups per CTA.  Measured on the large scene: 4 groups 9.70, 5: 10.34, 6: 9.92, 7: 9.69 G rays/s
@@ -509,6 +509,32 @@ int r1_scene_get_camera(const r1_scene *scene, float *out)
     return R1_OK;
 }
 
+// The sphere operand of the tensor-core filter (r1_tensor.cuh): n32 rows of 128 bytes, spheres that can never be hit and the
+// padding up to a multiple of 32 as rows no ray can flag.  Host arithmetic only.
+static void build_tensor_operand(const r1_scene *scene, unsigned char *dst, int n32)
+{
+    const int n = (int)scene->cx.size();
+    memset(dst, 0, (size_t)n32 * r1::tc::kRowBytes);
+    for (int i = 0; i < n32; ++i) {
+        const bool real = i < n && scene->inv_radius[i] != 0;      // rayweek1.cpp:288-292: inv_radius == 0 spheres never hit
+        r1::tc::sphere_row_host(dst, i, real, real ? scene->cx[i] : 0.0, real ? scene->cy[i] : 0.0, real ? scene->cz[i] : 0.0,
+                                real ? scene->radius_sq[i] : 0.0);
+    }
+}
+
+int r1_tensor_operand(const r1_scene *scene, void *out, uint64_t out_bytes, uint32_t *n32_out)
+{
+    if (!scene) return fail(R1_ERR_ARG, "null scene");
+    const int n32 = ((int)scene->cx.size() + 31) / 32 * 32;
+    if (n32_out) *n32_out = (uint32_t)n32;
+    if (n32 == 0 || n32 > r1::tc::kMaxSpheres) return fail(R1_ERR_LIMIT, "the tensor-core filter takes 1 .. %d spheres (this scene pads to %d)", r1::tc::kMaxSpheres, n32);
+    if (!out) return R1_OK;                                        // size query
+    if (out_bytes < (uint64_t)n32 * r1::tc::kRowBytes) return fail(R1_ERR_ARG, "operand buffer too small: %llu < %llu bytes", (unsigned long long)out_bytes,
+                                                                   (unsigned long long)n32 * r1::tc::kRowBytes);
+    build_tensor_operand(scene, static_cast<unsigned char *>(out), n32);
+    return R1_OK;
+}
+
 int r1_scene_commit(r1_scene *scene, int device)
 {
     if (!scene) return fail(R1_ERR_ARG, "null scene");
@@ -536,7 +562,7 @@ int r1_scene_commit(r1_scene *scene, int device)
     const float inf = std::numeric_limits<float>::infinity();
     // host image of the device block: [scan n_pad f4 | exact n_pad f4 | shade n_pad x 2 f4 | tensor-filter operand n32 x 128 B]
     const int n32 = (n + 31) / 32 * 32;
-    const bool tensor_ok = n32 <= r1::tc::kMaxSpheres;
+    const bool tensor_ok = n32 > 0 && n32 <= r1::tc::kMaxSpheres;
     const size_t tcb_off = (size_t)n_pad * (16 + 16 + 32);
     const size_t bytes = tcb_off + (tensor_ok ? (size_t)n32 * r1::tc::kRowBytes : 0);
     std::vector<unsigned char> host(bytes, 0);
@@ -577,12 +603,7 @@ int r1_scene_commit(r1_scene *scene, int device)
         }
         shade[2 * i + 1] = make_float4(inv_r, kind_bits, inv_ior, r0s);
     }
-    if (tensor_ok)
-        for (int i = 0; i < n32; ++i) {
-            const bool real = i < n && scene->inv_radius[i] != 0;
-            r1::tc::sphere_row_host(host.data() + tcb_off, i, real, real ? scene->cx[i] : 0.0, real ? scene->cy[i] : 0.0, real ? scene->cz[i] : 0.0,
-                                    real ? scene->radius_sq[i] : 0.0);
-        }
+    if (tensor_ok) build_tensor_operand(scene, host.data() + tcb_off, n32);
     rc = take_scene_block(*scr, bytes, &c.block, &c.block_bytes);
     if (rc) return rc;
     {
@@ -885,7 +906,7 @@ int r1_filter_probe(r1_scene *scene, int n, const float *org, const float *dir, 
     R1_TRY(get_ctx(scene, &cp));
     if (n < 0 || (n > 0 && (!org || !dir || !e))) return fail(R1_ERR_ARG, "bad argument");
     if (n == 0) return R1_OK;
-    if (!cp->dev.tcb) return fail(R1_ERR_LIMIT, "the tensor-core filter keeps at most %d spheres in shared memory", r1::tc::kMaxSpheres);
+    if (!cp->dev.tcb) return fail(R1_ERR_LIMIT, "the tensor-core filter takes scenes of 1 .. %d spheres (its operand lives in shared memory)", r1::tc::kMaxSpheres);
     const int n32 = cp->dev.n32;
     DevBuf d_org, d_dir, d_e;
     R1_TRY(d_org.upload(org, (size_t)n * 12)); R1_TRY(d_dir.upload(dir, (size_t)n * 12));

@@ -468,6 +468,8 @@ def main():
         tmem_bps = tests * 4 / (ms_trace * 1e-3)
         roofline["note"] = ("frac > 1 is not an error: the filter (8 of the reference's 10 FMA-pipe instructions per test) runs as a split-TF32 "
                             "GEMM on the tensor cores; see `tensor` and `tmem_read` for the hardware bounds of this kernel")
+        roofline["limiter"] = ("latency: no unit saturated (ncu of the large scene: issue slots 61 %, ALU pipe 59 %, tensor pipe 50 %, TMEM reads "
+                               "31 %; 26 % of the stall samples wait for an accumulator chunk) -- profiles/r02_ncu_megakernel_tc3.md")
         roofline["tensor"] = {"executed": tf32_exec, "peak": tf32_peak, "unit": "TFLOP/s", "frac": tf32_exec / tf32_peak,
                               "peak_source": "MEASURED_PEAKS.json sustained dense bf16 / 2" if bf16_peak else "nominal dense TF32 (half of 2.25 PFLOP/s bf16)",
                               "flops_model": "2 x K = 32 (11 lifted features x {hi hi, lo hi, hi lo}) per ray-sphere test, %d columns per ray" % n32}

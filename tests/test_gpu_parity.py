@@ -700,6 +700,26 @@ def test_scene_above_staging_limit(r1, tmp_path):
     s.close()
 
 
+def test_tensor_variant_with_a_ragged_last_chunk(r1, tmp_path):
+    """676 spheres = 5 accumulator chunks of 128 + one of 64 (and 36 of 704 rows padding): the default variant resolves to the
+    tensor kernel and renders the same bytes as the FFMA2 kernel, whole and as rank 1 of 3"""
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_scene
+    cam, sph = make_scene.grid_scene(28, 24, 480, (9, 6, 16), 14.0)
+    path = str(tmp_path / "mid.r1scene")
+    r1.write_scene_file(path, cam, sph)
+    s = r1.create_scene_from_file(path)
+    assert s.count() == 680 and r1.lib.r1_kernel_name(s.handle, r1.VARIANT_MEGAKERNEL).decode() == "megakernel_tc3"
+    base, r0 = s.render(120, 68, 12, variant=r1.VARIANT_MEGAKERNEL_PACKED)
+    alt, ra = s.render(120, 68, 12)
+    assert np.array_equal(base, alt) and ra.num_rays == r0.num_rays and base.any()
+    part, _ = s.render(120, 68, 12, rank=1, world=3)
+    assert np.array_equal(part, base[[r1.global_row(lr, r1.DEFAULT_ROW_TILE, 1, 3) for lr in range(part.shape[0])]])
+    s.close()
+
+
 @pytest.mark.parametrize("name", ALL)
 def test_per_pixel_replay_matches_reference_color(r1, scenes, golden_rays, name):
     """the GPU integrator (production scan / exact test / scatter / sky, the reference's generators replayed
